@@ -1,0 +1,177 @@
+/*
+ * iwb200.h -- C-ABI of the B200-native energy-condition engine (libiwb200.so).
+ *
+ * The reference (DawsonInstitute/irrotational-warp-lab) is pure Python and has no
+ * FFI; its seam for this path is the keyword-only contract of three functions and
+ * one backend registry.  Each entry point below replaces the array work of one of
+ * them; the Python host (irrotational-warp-lab_b200/backend.py) keeps the
+ * reference's signatures and return objects and calls these through ctypes.
+ *
+ *   iwb_energy3d*        <- compute_energy_3d      scripts/reproduce_rodal_exact.py:157-235
+ *                           + phi_exact_rodal      src/irrotational_warp/potential.py:80-99
+ *                           + g_rodal_exact        src/irrotational_warp/potential.py:37-77
+ *                           + _split_pos_neg       scripts/reproduce_rodal_exact.py:57-61
+ *                           + the _e_at_r closure  scripts/reproduce_rodal_exact.py:220-224
+ *   iwb_energy_axisym    <- compute_energy_axisymmetric  scripts/reproduce_rodal_exact.py:76-154
+ *   iwb_slice_z0         <- compute_slice_z0       src/irrotational_warp/adm.py:27-88
+ *                           + central_diff_2d      src/irrotational_warp/fd.py:6-25
+ *                           + integrate_signed     src/irrotational_warp/adm.py:91-97
+ *   iwb_energy3d_batch   <- the serial loops of sweep_velocity
+ *                           scripts/sweep_superluminal.py:59-106 and grid_search
+ *                           src/irrotational_warp/optimize.py:100-114
+ *   iwb_create/device_count/last_error <- _resolve_backend
+ *                           scripts/reproduce_rodal_exact.py:16-30
+ *
+ * Conventions: plain C, no torch / CUDA types.  All pointers are caller-owned
+ * HOST memory unless a field says "device"; the library copies what it needs and
+ * keeps nothing past return.  Every call is blocking and returns IWB_OK (0) or an
+ * error code; iwb_last_error() gives the thread-local message.  A handle is bound
+ * to ONE device (one process per GPU is the multi-GPU model; the host layer does
+ * the NCCL collective through torch.distributed) and is not thread-safe; use one
+ * handle per thread.  There is no CPU fallback: without a usable sm_100 device
+ * iwb_create fails.
+ */
+#ifndef IWB200_H
+#define IWB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IWB_VERSION 100          /* 0.1.0 */
+#define IWB_MAX_SHELLS 8
+
+enum iwb_status {
+    IWB_OK = 0,
+    IWB_ERR_INVALID = 1,         /* bad argument (maps to Python ValueError)        */
+    IWB_ERR_GRID_TOO_SMALL = 2,  /* < edge_order+1 points on an axis (numpy.gradient's ValueError) */
+    IWB_ERR_NO_DEVICE = 3,       /* no usable GPU (maps to RuntimeError, like a failed CuPy import) */
+    IWB_ERR_CUDA = 4,            /* CUDA runtime error, see iwb_last_error()        */
+    IWB_ERR_NOMEM = 5
+};
+
+/* arithmetic variants */
+enum iwb_dtype {
+    IWB_F64 = 0,       /* reference --dtype float64                                          */
+    IWB_F32_REF = 1,   /* reference --dtype float32 as NumPy>=2 evaluates it: float32 grid,   */
+                       /* r, log-cosh and cos(theta); float64 from sinh(rho*sigma) onwards    */
+    IWB_F32_STRICT = 2 /* everything in float32 (documented as outside the 1e-5 bar at large n) */
+};
+
+enum iwb_mode {
+    IWB_MODE_EXACT = 0, /* IEEE replay of the reference's operation order (bit-exact masks/counts) */
+    IWB_MODE_FAST = 1   /* FMA contraction + reciprocal multiplies; energies within 1e-10       */
+};
+
+typedef struct iwb_handle iwb_handle;
+
+/* One 3D evaluation.  The grid is n0 x n1 x n2 points, C order [i, j, k] like the
+ * reference's meshgrid(indexing="ij"); x, y, z are the host linspace arrays and
+ * dx, dy, dz the host-computed float(x[1]-x[0]) (reproduce_rodal_exact.py:171-177).
+ * For IWB_F32_REF the arrays hold float32-rounded values widened to double. */
+typedef struct {
+    int32_t dtype;             /* enum iwb_dtype */
+    int32_t mode;              /* enum iwb_mode  */
+    int32_t n0, n1, n2;
+    int32_t i_begin, i_end;    /* planes of axis 0 to evaluate: [i_begin, i_end) of the GLOBAL grid.
+                                  (0, n0) = whole volume.  A slab gets its 2-plane phi halo by
+                                  analytic recomputation from the global coordinates.            */
+    const double *x, *y, *z;   /* host, lengths n0, n1, n2 */
+    double dx, dy, dz;
+    double rho, sigma, v, eps; /* eps = 1e-12 in the reference (potential.py:88) */
+    double sinh_rs, cosh_rs;   /* np.sinh / np.cosh(rho*sigma) computed by the host (potential.py:50-52) */
+    int32_t nshell;            /* <= IWB_MAX_SHELLS */
+    double shell_r[IWB_MAX_SHELLS]; /* radii for the inclusive masks r <= R (the _e_at_r closure) */
+    double *rho_out;           /* NULL, or [i_end-i_begin, n1, n2] doubles receiving rho_adm          */
+    int32_t rho_out_is_device; /* 1: rho_out is a device pointer on the handle's device             */
+} iwb_params3d;
+
+typedef struct {
+    double e_pos, e_neg;                 /* sum e*[e>0], sum e*[e<0] (negative), e = rho_adm*dV */
+    int64_t cnt_pos, cnt_neg, cnt_zero, cnt_nan;
+    double shell_pos[IWB_MAX_SHELLS], shell_neg[IWB_MAX_SHELLS];
+    int64_t shell_cnt[IWB_MAX_SHELLS];   /* points with r <= R */
+    double kernel_ms;                    /* CUDA-event time of the fused kernel + final reduction */
+    double total_ms;                     /* host wall time of the call */
+} iwb_result;
+
+/* Fixed-layout partial sums of one slab, for the shard-count-independent reduction:
+ * one row per "flush block" of IWB_FLUSH_PLANES planes of axis 0, IWB_ROW_WIDTH doubles per row
+ * (int64 counts are stored bit-cast in double slots).  See DESIGN.md §5. */
+#define IWB_FLUSH_PLANES 16
+#define IWB_ROW_WIDTH (6 + 3 * IWB_MAX_SHELLS)   /* e_pos e_neg cnt_pos cnt_neg cnt_zero cnt_nan | shell_pos[8] shell_neg[8] shell_cnt[8] */
+
+int iwb_version(void);
+int iwb_device_count(void);
+const char *iwb_last_error(void);
+
+/* device_id: CUDA ordinal.  Fails with IWB_ERR_NO_DEVICE when there is none or it is not sm_100. */
+int iwb_create(int device_id, iwb_handle **out);
+int iwb_destroy(iwb_handle *h);
+int iwb_device_info(iwb_handle *h, int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len);
+
+/* Whole evaluation: kernel, deterministic final reduction, D2H of the scalars. */
+int iwb_energy3d(iwb_handle *h, const iwb_params3d *p, iwb_result *out);
+
+/* Slab evaluation for the multi-GPU path.  Writes the per-flush-block table
+ * rows [i_begin/IWB_FLUSH_PLANES, ceil(i_end/IWB_FLUSH_PLANES)) x IWB_ROW_WIDTH into
+ * `table_device` (DEVICE pointer to the full [ceil(n0/IWB_FLUSH_PLANES), IWB_ROW_WIDTH] table; rows of
+ * other slabs are not touched) on `stream` (a cudaStream_t passed as void*, NULL = the handle's
+ * stream) WITHOUT synchronising.  i_begin must be a multiple of IWB_FLUSH_PLANES. */
+int iwb_energy3d_slab_async(iwb_handle *h, const iwb_params3d *p, double *table_device, void *stream);
+
+/* Fixed-order sum of a complete table (device pointer) into *out; blocking. */
+int iwb_reduce_table(iwb_handle *h, const double *table_device, int nrows, int nshell, void *stream,
+                     iwb_result *out);
+
+/* Independent parameter points on one device; one host synchronisation at the end. */
+int iwb_energy3d_batch(iwb_handle *h, int npoints, const iwb_params3d *pts, iwb_result *outs);
+
+/* Axisymmetric half-plane, arrays [ny, nx] (x fastest), z = 0. */
+typedef struct {
+    int32_t dtype, mode;
+    int32_t nx, ny;
+    const double *x, *y;       /* host, lengths nx, ny */
+    double dx, dy;
+    double rho, sigma, v, eps;
+    double sinh_rs, cosh_rs;
+    int32_t nshell;
+    double shell_r[IWB_MAX_SHELLS];
+    double *rho_out;           /* NULL or host [ny, nx] */
+} iwb_params_axisym;
+
+int iwb_energy_axisym(iwb_handle *h, const iwb_params_axisym *p, iwb_result *out);
+
+/* 2D z=0 slice with the tanh-wall dipole potential and edge_order=1 differences.
+ * All four field buffers are host [n, n] doubles in [y, x] order and must be non-NULL
+ * (SliceResult carries them).  pos / neg / net follow integrate_signed: neg >= 0. */
+typedef struct {
+    int32_t n;
+    const double *x, *y;
+    double dx, dy;
+    double rho, sigma, v, eps;
+    double *phi, *beta_x, *beta_y, *rho_adm;
+} iwb_params_slice;
+
+typedef struct {
+    double pos, neg, net;
+    int64_t cnt_pos, cnt_neg, cnt_zero;
+    double kernel_ms, total_ms;
+} iwb_slice_result;
+
+int iwb_slice_z0(iwb_handle *h, const iwb_params_slice *p, iwb_slice_result *out);
+
+/* Measured FP64 / FP32 FMA pipe peak of the handle's device (register-resident microbenchmark),
+ * in TFLOP/s counting 2 flops per FMA; used as the roofline denominator by bench.py. */
+int iwb_measure_fma_peak(iwb_handle *h, int use_fp32, double *tflops, double *sm_mhz_effective);
+
+/* Test hook: compares the constant-divisor division used by the exact kernels with IEEE division
+ * on `count` pseudo-random numerators; returns the number of mismatching results in *mismatches. */
+int iwb_selftest_constdiv(iwb_handle *h, double divisor, uint64_t count, uint64_t seed, uint64_t *mismatches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IWB200_H */

@@ -1,0 +1,137 @@
+"""ctypes binding of ``libiwb200.so`` (declarations mirror ``include/iwb200.h``).
+
+The library is the product: if it is missing or fails to load there is NO fallback --
+importing this module raises, and so does every evaluator of the ``b200`` backend.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libiwb200.so")
+
+MAX_SHELLS = 8
+FLUSH_PLANES = 16
+ROW_WIDTH = 6 + 3 * MAX_SHELLS
+
+OK, ERR_INVALID, ERR_GRID_TOO_SMALL, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM = range(6)
+F64, F32_REF, F32_STRICT = 0, 1, 2
+MODE_EXACT, MODE_FAST = 0, 1
+
+_dp = C.POINTER(C.c_double)
+
+
+class Params3D(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("mode", C.c_int32),
+        ("n0", C.c_int32), ("n1", C.c_int32), ("n2", C.c_int32),
+        ("i_begin", C.c_int32), ("i_end", C.c_int32),
+        ("x", _dp), ("y", _dp), ("z", _dp),
+        ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
+        ("rho", C.c_double), ("sigma", C.c_double), ("v", C.c_double), ("eps", C.c_double),
+        ("sinh_rs", C.c_double), ("cosh_rs", C.c_double),
+        ("nshell", C.c_int32),
+        ("shell_r", C.c_double * MAX_SHELLS),
+        ("rho_out", C.c_void_p),
+        ("rho_out_is_device", C.c_int32),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("e_pos", C.c_double), ("e_neg", C.c_double),
+        ("cnt_pos", C.c_int64), ("cnt_neg", C.c_int64), ("cnt_zero", C.c_int64), ("cnt_nan", C.c_int64),
+        ("shell_pos", C.c_double * MAX_SHELLS), ("shell_neg", C.c_double * MAX_SHELLS),
+        ("shell_cnt", C.c_int64 * MAX_SHELLS),
+        ("kernel_ms", C.c_double), ("total_ms", C.c_double),
+    ]
+
+
+class ParamsAxisym(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("mode", C.c_int32),
+        ("nx", C.c_int32), ("ny", C.c_int32),
+        ("x", _dp), ("y", _dp),
+        ("dx", C.c_double), ("dy", C.c_double),
+        ("rho", C.c_double), ("sigma", C.c_double), ("v", C.c_double), ("eps", C.c_double),
+        ("sinh_rs", C.c_double), ("cosh_rs", C.c_double),
+        ("nshell", C.c_int32),
+        ("shell_r", C.c_double * MAX_SHELLS),
+        ("rho_out", _dp),
+    ]
+
+
+class ParamsSlice(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32),
+        ("x", _dp), ("y", _dp),
+        ("dx", C.c_double), ("dy", C.c_double),
+        ("rho", C.c_double), ("sigma", C.c_double), ("v", C.c_double), ("eps", C.c_double),
+        ("phi", _dp), ("beta_x", _dp), ("beta_y", _dp), ("rho_adm", _dp),
+    ]
+
+
+class SliceResultC(C.Structure):
+    _fields_ = [
+        ("pos", C.c_double), ("neg", C.c_double), ("net", C.c_double),
+        ("cnt_pos", C.c_int64), ("cnt_neg", C.c_int64), ("cnt_zero", C.c_int64),
+        ("kernel_ms", C.c_double), ("total_ms", C.c_double),
+    ]
+
+
+# every symbol include/iwb200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "iwb_version": (C.c_int, []),
+    "iwb_device_count": (C.c_int, []),
+    "iwb_last_error": (C.c_char_p, []),
+    "iwb_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "iwb_destroy": (C.c_int, [C.c_void_p]),
+    "iwb_device_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.c_char_p, C.c_int]),
+    "iwb_energy3d": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.POINTER(Result)]),
+    "iwb_energy3d_slab_async": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.c_void_p, C.c_void_p]),
+    "iwb_reduce_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(Result)]),
+    "iwb_energy3d_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Params3D), C.POINTER(Result)]),
+    "iwb_energy_axisym": (C.c_int, [C.c_void_p, C.POINTER(ParamsAxisym), C.POINTER(Result)]),
+    "iwb_slice_z0": (C.c_int, [C.c_void_p, C.POINTER(ParamsSlice), C.POINTER(SliceResultC)]),
+    "iwb_measure_fma_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "iwb_selftest_constdiv": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library; raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python irrotational-warp-lab_b200/build.py` "
+            "(the b200 backend has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)       # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().iwb_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    """Map status codes to the reference's exception types
+    (reproduce_rodal_exact.py:25-30; numpy.gradient's ValueError)."""
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc in (ERR_INVALID, ERR_GRID_TOO_SMALL):
+        raise ValueError(msg)
+    if rc == ERR_NOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)

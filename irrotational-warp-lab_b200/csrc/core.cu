@@ -1,0 +1,232 @@
+// Handle lifetime, error reporting, host-side scalar preparation, FMA-peak microbenchmark.
+// Interface replaced: _resolve_backend (/root/reference/scripts/reproduce_rodal_exact.py:16-30).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "host_common.h"
+
+namespace iwb {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+// numpy.gradient's scalars for a uniform axis (numpy/lib/_function_base_impl.py):
+// 2.*h, and a,b,c of both one-sided second-order formulas, each one IEEE operation.
+AxisCoef make_axis_coef(double h)
+{
+    AxisCoef c;
+    c.h2 = 2. * h;
+    c.rh2 = 1.0 / c.h2;
+    c.a0 = -1.5 / h; c.b0 = 2. / h; c.c0 = -0.5 / h;
+    c.a1 = 0.5 / h;  c.b1 = -2. / h; c.c1 = 1.5 / h;
+    return c;
+}
+
+// Largest s with RN(sqrt(s)) <= R: the reference's inclusive mask r_grid <= R
+// (reproduce_rodal_exact.py:221) applied to s = (x*x + y*y) + z*z before the square root.
+// RN(sqrt) is monotone, so the two tests select exactly the same points.
+double shell_threshold_f64(double R)
+{
+    if (!(R >= 0.0)) return -1.0;
+    if (isinf(R)) return INFINITY;
+    double s = R * R;
+    while (!isinf(s) && sqrt(nextafter(s, INFINITY)) <= R) s = nextafter(s, INFINITY);
+    while (s > 0.0 && sqrt(s) > R) s = nextafter(s, -INFINITY);
+    return s;
+}
+
+// float32 grid: r and the comparison are float32 (r_lim is a weak Python scalar -> float32)
+double shell_threshold_f32(double R)
+{
+    float Rf = (float)R;
+    if (!(Rf >= 0.0f)) return -1.0;
+    if (isinf(Rf)) return INFINITY;
+    float s = Rf * Rf;
+    while (!isinf(s) && sqrtf(nextafterf(s, INFINITY)) <= Rf) s = nextafterf(s, INFINITY);
+    while (s > 0.0f && sqrtf(s) > Rf) s = nextafterf(s, -INFINITY);
+    return (double)s;
+}
+
+PhiConst make_phi_const(double rho, double sigma, double v, double eps, double sinh_rs, double cosh_rs)
+{
+    PhiConst c;
+    c.sigma = sigma; c.sigma2 = 2.0 * sigma; c.rho = rho; c.v = v; c.eps = eps;
+    c.S = sinh_rs; c.C = cosh_rs;
+    c.sigf = (float)sigma; c.sig2f = 2.0f * (float)sigma; c.rhof = (float)rho; c.vf = (float)v; c.epsf = (float)eps;
+    return c;
+}
+
+// ---- register-resident FMA throughput (roofline denominator) -------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_fma_peak(T* sink, int iters, T a, T b)
+{
+    T v0 = (T)threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+            v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+        }
+    }
+    T r = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+    if (r == (T)123456789) sink[0] = r;   // never true; keeps the chain alive
+}
+
+// ---- constant-divisor division self-test -----------------------------------------------------------
+__global__ void k_selftest_constdiv(double d, double rd, uint64_t count, uint64_t seed, unsigned long long* mism)
+{
+    uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (uint64_t n = tid; n < count; n += stride) {
+        // splitmix64 -> random sign/exponent in [2^-40, 2^40) / mantissa
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (n + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        uint64_t mant = z & 0x000FFFFFFFFFFFFFull;
+        uint64_t expo = 1023 - 40 + ((z >> 52) % 80);
+        uint64_t sign = z >> 63;
+        double a = __longlong_as_double((long long)((sign << 63) | (expo << 52) | mant));
+        if (cdiv(a, d, rd) != a / d) ++bad;
+    }
+    if (bad) atomicAdd(mism, bad);
+}
+
+}  // namespace iwb
+
+using namespace iwb;
+
+extern "C" {
+
+int iwb_version(void) { return IWB_VERSION; }
+
+const char* iwb_last_error(void) { return g_last_error.c_str(); }
+
+int iwb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int iwb_create(int device_id, iwb_handle** out)
+{
+    if (!out) return fail(IWB_ERR_INVALID, "iwb_create: out is NULL");
+    *out = nullptr;
+    int n = iwb_device_count();
+    if (n <= 0)
+        return fail(IWB_ERR_NO_DEVICE, "b200 backend requested but no CUDA device is visible "
+                                       "(there is no CPU fallback; use backend='numpy' for the reference path)");
+    if (device_id < 0 || device_id >= n) return fail(IWB_ERR_INVALID, "iwb_create: device_id out of range");
+    iwb_handle* h = new iwb_handle();
+    h->device = device_id;
+    IWB_CUDA(cudaSetDevice(device_id));
+    IWB_CUDA(cudaGetDeviceProperties(&h->prop, device_id));
+    if (h->prop.major != 10) {
+        std::string nm = h->prop.name;
+        delete h;
+        return fail(IWB_ERR_NO_DEVICE, "b200 backend needs an sm_100 device, found " + nm);
+    }
+    h->sm_count = h->prop.multiProcessorCount;
+    for (int s = 0; s < NSCRATCH; ++s) {
+        IWB_CUDA(cudaStreamCreateWithFlags(&h->scr[s].stream, cudaStreamNonBlocking));
+        IWB_CUDA(cudaEventCreate(&h->scr[s].ev0));
+        IWB_CUDA(cudaEventCreate(&h->scr[s].ev1));
+    }
+    const char* cfg = getenv("IWB_K3_CONFIG");
+    h->k3_config = cfg ? atoi(cfg) : 0;
+    const char* sl = getenv("IWB_K3_SEG_LEN");
+    h->k3_seg_len = sl ? atoi(sl) : 0;
+    *out = h;
+    return IWB_OK;
+}
+
+int iwb_destroy(iwb_handle* h)
+{
+    if (!h) return IWB_OK;
+    cudaSetDevice(h->device);
+    for (int s = 0; s < NSCRATCH; ++s) {
+        Scratch& c = h->scr[s];
+        if (c.stream) cudaStreamSynchronize(c.stream);
+        c.coords.release(); c.partial.release(); c.table.release(); c.out.release(); c.rho.release();
+        c.h_coords.release(); c.h_out.release();
+        if (c.ev0) cudaEventDestroy(c.ev0);
+        if (c.ev1) cudaEventDestroy(c.ev1);
+        if (c.stream) cudaStreamDestroy(c.stream);
+    }
+    delete h;
+    return IWB_OK;
+}
+
+int iwb_device_info(iwb_handle* h, int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len)
+{
+    if (!h) return fail(IWB_ERR_INVALID, "null handle");
+    if (sm_count) *sm_count = h->sm_count;
+    if (cc_major) *cc_major = h->prop.major;
+    if (cc_minor) *cc_minor = h->prop.minor;
+    if (name && name_len > 0) {
+        strncpy(name, h->prop.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    return IWB_OK;
+}
+
+int iwb_measure_fma_peak(iwb_handle* h, int use_fp32, double* tflops, double* sm_mhz_effective)
+{
+    if (!h || !tflops) return fail(IWB_ERR_INVALID, "iwb_measure_fma_peak: null argument");
+    IWB_CUDA(cudaSetDevice(h->device));
+    Scratch& c = h->scr[0];
+    IWB_CUDA(c.out.reserve(ROW_BYTES_MIN));
+    const int grid = h->sm_count * 8, block = 256, iters = 4096;
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 6; ++rep) {
+        IWB_CUDA(cudaEventRecord(c.ev0, c.stream));
+        if (use_fp32) k_fma_peak<float><<<grid, block, 0, c.stream>>>((float*)c.out.p, iters, 1.0000001f, 1e-9f);
+        else k_fma_peak<double><<<grid, block, 0, c.stream>>>((double*)c.out.p, iters, 1.0000000001, 1e-12);
+        IWB_CUDA(cudaEventRecord(c.ev1, c.stream));
+        IWB_CUDA(cudaEventSynchronize(c.ev1));
+        IWB_CUDA(cudaGetLastError());
+        float ms = 0;
+        IWB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    const double fmas = (double)grid * block * (double)iters * 64.0;
+    *tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
+    if (sm_mhz_effective) {
+        const double lanes = use_fp32 ? 128.0 : 64.0;
+        *sm_mhz_effective = fmas / (best_ms * 1e-3) / (h->sm_count * lanes) / 1e6;
+    }
+    return IWB_OK;
+}
+
+int iwb_selftest_constdiv(iwb_handle* h, double divisor, uint64_t count, uint64_t seed, uint64_t* mismatches)
+{
+    if (!h || !mismatches) return fail(IWB_ERR_INVALID, "iwb_selftest_constdiv: null argument");
+    IWB_CUDA(cudaSetDevice(h->device));
+    Scratch& c = h->scr[0];
+    IWB_CUDA(c.out.reserve(ROW_BYTES_MIN));
+    IWB_CUDA(cudaMemsetAsync(c.out.p, 0, 8, c.stream));
+    k_selftest_constdiv<<<h->sm_count * 8, 256, 0, c.stream>>>(divisor, 1.0 / divisor, count, seed,
+                                                              (unsigned long long*)c.out.p);
+    IWB_CUDA(cudaGetLastError());
+    unsigned long long bad = 0;
+    IWB_CUDA(cudaMemcpyAsync(&bad, c.out.p, 8, cudaMemcpyDeviceToHost, c.stream));
+    IWB_CUDA(cudaStreamSynchronize(c.stream));
+    *mismatches = bad;
+    return IWB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,291 @@
+// C-ABI entry points of the fused 3D evaluator.  Compiled with -fmad=false (IEEE replay).
+// Interfaces replaced: compute_energy_3d + the _e_at_r closure + _split_pos_neg
+// (/root/reference/scripts/reproduce_rodal_exact.py:157-235, 57-61) and the loops of
+// sweep_velocity (/root/reference/scripts/sweep_superluminal.py:59-106).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+#include <string>
+
+#include "energy3d.cuh"
+#include "host_common.h"
+
+namespace iwb {
+
+// ---- kernel geometry variants -----------------------------------------------------------------
+//   config 0: region 32 x 64, 8 warps, 128 KB smem, 1 CTA / SM
+//   config 1: region 24 x 64, 6 warps,  96 KB smem, 2 CTAs / SM
+struct K3Config { int rj, nw; };
+static const K3Config kConfigs[] = {{32, 8}, {24, 6}};
+constexpr int kNumConfigs = 2;
+
+template <int DT, int NSH, int RJ, int NW, bool EMIT>
+static cudaError_t launch_one(const K3Params& P, int sm_count, cudaStream_t st)
+{
+    auto kern = k_energy3d<DT, NSH, RJ, NW, EMIT>;
+    constexpr size_t smem = Geo<RJ, NW>::SMEM_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    int grid = sm_count * per_sm;
+    if (grid > P.nitems) grid = P.nitems;
+    kern<<<grid, NW * 32, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+template <int DT, int NSH, bool EMIT>
+static cudaError_t launch_cfg(int cfg, const K3Params& P, int sm_count, cudaStream_t st)
+{
+    switch (cfg) {
+    case 1: return launch_one<DT, NSH, 24, 6, EMIT>(P, sm_count, st);
+    default: return launch_one<DT, NSH, 32, 8, EMIT>(P, sm_count, st);
+    }
+}
+
+template <int DT, bool EMIT>
+static cudaError_t launch_nsh(int nshell, int cfg, const K3Params& P, int sm_count, cudaStream_t st)
+{
+    if (nshell <= 2) return launch_cfg<DT, 2, EMIT>(cfg, P, sm_count, st);
+    return launch_cfg<DT, IWB_MAX_SHELLS, EMIT>(cfg, P, sm_count, st);
+}
+
+static cudaError_t launch_k3(int dtype, int nshell, bool emit, int cfg, const K3Params& P, int sm_count, cudaStream_t st)
+{
+    if (dtype == IWB_F64)
+        return emit ? launch_nsh<IWB_F64, true>(nshell, cfg, P, sm_count, st)
+                    : launch_nsh<IWB_F64, false>(nshell, cfg, P, sm_count, st);
+    return emit ? launch_nsh<IWB_F32_REF, true>(nshell, cfg, P, sm_count, st)
+                : launch_nsh<IWB_F32_REF, false>(nshell, cfg, P, sm_count, st);
+}
+
+static int validate(const iwb_params3d* p)
+{
+    if (!p) return fail(IWB_ERR_INVALID, "params is NULL");
+    if (p->dtype != IWB_F64 && p->dtype != IWB_F32_REF)
+        return fail(IWB_ERR_INVALID, "energy3d: dtype must be IWB_F64 or IWB_F32_REF (IWB_F32_STRICT is not built yet)");
+    if (p->mode != IWB_MODE_EXACT) return fail(IWB_ERR_INVALID, "energy3d: only IWB_MODE_EXACT is built");
+    if (p->n0 < 3 || p->n1 < 3 || p->n2 < 3)
+        return fail(IWB_ERR_GRID_TOO_SMALL, "Shape of array too small to calculate a numerical gradient, "
+                                            "at least (edge_order + 1) elements are required.");
+    if (!p->x || !p->y || !p->z) return fail(IWB_ERR_INVALID, "energy3d: coordinate arrays are NULL");
+    if (p->i_begin < 0 || p->i_end > p->n0 || p->i_begin >= p->i_end)
+        return fail(IWB_ERR_INVALID, "energy3d: need 0 <= i_begin < i_end <= n0");
+    if (p->i_begin % IWB_FLUSH_PLANES != 0)
+        return fail(IWB_ERR_INVALID, "energy3d: i_begin must be a multiple of IWB_FLUSH_PLANES");
+    if (p->nshell < 0 || p->nshell > IWB_MAX_SHELLS) return fail(IWB_ERR_INVALID, "energy3d: nshell out of range");
+    if (!(p->dx > 0.0) || !(p->dy > 0.0) || !(p->dz > 0.0)) return fail(IWB_ERR_INVALID, "energy3d: spacings must be > 0");
+    return IWB_OK;
+}
+
+// Uploads coordinates, fills K3Params and launches the fused kernel + the tile reduction on c.stream.
+// `table` is the [ceil(n0/FLUSH)][ROW] device table; only the rows of [i_begin, i_end) are written.
+static int enqueue_slab(iwb_handle* h, Scratch& c, const iwb_params3d* p, double* table, cudaStream_t st,
+                        double* rho_dev)
+{
+    const int n0 = p->n0, n1 = p->n1, n2 = p->n2;
+    const K3Config cfg = kConfigs[(h->k3_config >= 0 && h->k3_config < kNumConfigs) ? h->k3_config : 0];
+    const int cfg_id = (h->k3_config >= 0 && h->k3_config < kNumConfigs) ? h->k3_config : 0;
+
+    // coordinates: x, x*x, y*y, z*z (squares rounded once in the coordinate dtype, as x*x is in NumPy)
+    const size_t ncoord = (size_t)2 * n0 + n1 + n2;
+    IWB_CUDA(c.h_coords.reserve(ncoord * sizeof(double)));
+    IWB_CUDA(c.coords.reserve(ncoord * sizeof(double)));
+    double* hc = (double*)c.h_coords.p;
+    double *hx = hc, *hxx = hc + n0, *hyy = hc + 2 * n0, *hzz = hc + 2 * n0 + n1;
+    if (p->dtype == IWB_F64) {
+        for (int i = 0; i < n0; ++i) { hx[i] = p->x[i]; hxx[i] = p->x[i] * p->x[i]; }
+        for (int j = 0; j < n1; ++j) hyy[j] = p->y[j] * p->y[j];
+        for (int k = 0; k < n2; ++k) hzz[k] = p->z[k] * p->z[k];
+    } else {
+        for (int i = 0; i < n0; ++i) { float f = (float)p->x[i]; hx[i] = f; hxx[i] = (double)(f * f); }
+        for (int j = 0; j < n1; ++j) { float f = (float)p->y[j]; hyy[j] = (double)(f * f); }
+        for (int k = 0; k < n2; ++k) { float f = (float)p->z[k]; hzz[k] = (double)(f * f); }
+    }
+    // the pinned staging buffer may still feed an earlier async copy on this stream
+    IWB_CUDA(cudaMemcpyAsync(c.coords.p, hc, ncoord * sizeof(double), cudaMemcpyHostToDevice, st));
+
+    K3Params P;
+    memset(&P, 0, sizeof(P));
+    P.n0 = n0; P.n1 = n1; P.n2 = n2;
+    P.i_begin = p->i_begin; P.i_end = p->i_end;
+    P.ntj = (n1 + (cfg.rj - 4) - 1) / (cfg.rj - 4);
+    P.ntk = (n2 + TK_MAX - 1) / TK_MAX;
+    const int ntiles = P.ntj * P.ntk;
+    const int planes = p->i_end - p->i_begin;
+    // planes per work item: whole slab unless that leaves the GPU under-filled / unbalanced
+    int seg_len = ((planes + FLUSH - 1) / FLUSH) * FLUSH;
+    if (h->k3_seg_len > 0) {
+        seg_len = ((h->k3_seg_len + FLUSH - 1) / FLUSH) * FLUSH;
+    } else {
+        const long long want = 6LL * h->sm_count;       // items for a balanced static schedule
+        while (seg_len > 2 * FLUSH && (long long)ntiles * ((planes + seg_len - 1) / seg_len) < want)
+            seg_len = ((seg_len / 2 + FLUSH - 1) / FLUSH) * FLUSH;
+        if ((long long)ntiles * ((planes + seg_len - 1) / seg_len) < h->sm_count && seg_len > FLUSH) seg_len = FLUSH;
+    }
+    P.seg_len = seg_len;
+    P.nseg = (planes + seg_len - 1) / seg_len;
+    P.nitems = P.nseg * ntiles;
+    double* dc = (double*)c.coords.p;
+    P.x = dc; P.xx = dc + n0; P.yy = dc + 2 * n0; P.zz = dc + 2 * n0 + n1;
+    P.pc = make_phi_const(p->rho, p->sigma, p->v, p->eps, p->sinh_rs, p->cosh_rs);
+    P.cx = make_axis_coef(p->dx); P.cy = make_axis_coef(p->dy); P.cz = make_axis_coef(p->dz);
+    P.dV = (p->dx * p->dy) * p->dz;
+    P.c16pi = 16.0 * 3.141592653589793;
+    P.rc16pi = 1.0 / P.c16pi;
+    for (int s = 0; s < IWB_MAX_SHELLS; ++s) {
+        if (s < p->nshell)
+            P.shell_thr[s] = (p->dtype == IWB_F64) ? shell_threshold_f64(p->shell_r[s]) : shell_threshold_f32(p->shell_r[s]);
+        else
+            P.shell_thr[s] = -1.0;
+    }
+    const int nfb_total = (n0 + FLUSH - 1) / FLUSH;
+    IWB_CUDA(c.partial.reserve((size_t)nfb_total * ntiles * ROW * sizeof(double)));
+    P.partial = (double*)c.partial.p;
+    P.rho_out = rho_dev;
+
+    cudaError_t e = launch_k3(p->dtype, p->nshell, rho_dev != nullptr, cfg_id, P, h->sm_count, st);
+    if (e != cudaSuccess) return fail(IWB_ERR_CUDA, std::string("k_energy3d launch: ") + cudaGetErrorString(e));
+    const int fb0 = p->i_begin / FLUSH, fb1 = (p->i_end + FLUSH - 1) / FLUSH;
+    k_reduce_tiles<<<fb1 - fb0, 128, 0, st>>>(P.partial, table, fb0, ntiles);
+    IWB_CUDA(cudaGetLastError());
+    return IWB_OK;
+}
+
+static void unpack_row(const double* row, int nshell, iwb_result* out)
+{
+    auto as_i64 = [](double d) { int64_t v; memcpy(&v, &d, 8); return v; };
+    out->e_pos = row[0]; out->e_neg = row[1];
+    out->cnt_pos = as_i64(row[2]); out->cnt_neg = as_i64(row[3]);
+    out->cnt_zero = as_i64(row[4]); out->cnt_nan = as_i64(row[5]);
+    for (int s = 0; s < IWB_MAX_SHELLS; ++s) {
+        const bool used = s < nshell;
+        out->shell_pos[s] = used ? row[6 + s] : 0.0;
+        out->shell_neg[s] = used ? row[6 + IWB_MAX_SHELLS + s] : 0.0;
+        out->shell_cnt[s] = used ? as_i64(row[6 + 2 * IWB_MAX_SHELLS + s]) : 0;
+    }
+}
+
+// enqueue a full evaluation on scratch c; results land in c.h_out after c.ev1
+static int enqueue_full(iwb_handle* h, Scratch& c, const iwb_params3d* p)
+{
+    const int nfb_total = (p->n0 + FLUSH - 1) / FLUSH;
+    IWB_CUDA(c.table.reserve((size_t)nfb_total * ROW * sizeof(double)));
+    IWB_CUDA(c.out.reserve(ROW_BYTES_MIN));
+    IWB_CUDA(c.h_out.reserve(ROW_BYTES_MIN));
+    double* rho_dev = nullptr;
+    const size_t rho_bytes = (size_t)(p->i_end - p->i_begin) * p->n1 * p->n2 * sizeof(double);
+    if (p->rho_out) {
+        if (p->rho_out_is_device) rho_dev = p->rho_out;
+        else {
+            IWB_CUDA(c.rho.reserve(rho_bytes));
+            rho_dev = (double*)c.rho.p;
+        }
+    }
+    IWB_CUDA(cudaEventRecord(c.ev0, c.stream));
+    int rc = enqueue_slab(h, c, p, (double*)c.table.p, c.stream, rho_dev);
+    if (rc) return rc;
+    const int fb0 = p->i_begin / FLUSH, fb1 = (p->i_end + FLUSH - 1) / FLUSH;
+    k_reduce_rows<<<1, 128, 0, c.stream>>>((const double*)c.table.p + (size_t)fb0 * ROW, (double*)c.out.p, fb1 - fb0);
+    IWB_CUDA(cudaGetLastError());
+    IWB_CUDA(cudaMemcpyAsync(c.h_out.p, c.out.p, ROW_BYTES_MIN, cudaMemcpyDeviceToHost, c.stream));
+    IWB_CUDA(cudaEventRecord(c.ev1, c.stream));
+    if (p->rho_out && !p->rho_out_is_device)
+        IWB_CUDA(cudaMemcpyAsync(p->rho_out, rho_dev, rho_bytes, cudaMemcpyDeviceToHost, c.stream));
+    return IWB_OK;
+}
+
+}  // namespace iwb
+
+using namespace iwb;
+
+extern "C" {
+
+int iwb_energy3d(iwb_handle* h, const iwb_params3d* p, iwb_result* out)
+{
+    if (!h || !out) return fail(IWB_ERR_INVALID, "iwb_energy3d: null argument");
+    int rc = validate(p);
+    if (rc) return rc;
+    auto t0 = std::chrono::steady_clock::now();
+    IWB_CUDA(cudaSetDevice(h->device));
+    Scratch& c = h->scr[0];
+    rc = enqueue_full(h, c, p);
+    if (rc) return rc;
+    IWB_CUDA(cudaStreamSynchronize(c.stream));
+    memset(out, 0, sizeof(*out));
+    unpack_row((const double*)c.h_out.p, p->nshell, out);
+    float ms = 0;
+    IWB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+    out->kernel_ms = ms;
+    out->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return IWB_OK;
+}
+
+int iwb_energy3d_slab_async(iwb_handle* h, const iwb_params3d* p, double* table_device, void* stream)
+{
+    if (!h || !table_device) return fail(IWB_ERR_INVALID, "iwb_energy3d_slab_async: null argument");
+    int rc = validate(p);
+    if (rc) return rc;
+    if (p->rho_out && !p->rho_out_is_device)
+        return fail(IWB_ERR_INVALID, "iwb_energy3d_slab_async: rho_out must be a device pointer");
+    IWB_CUDA(cudaSetDevice(h->device));
+    Scratch& c = h->scr[0];
+    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    // the staging buffer of scratch 0 is reused: make sure the previous upload from it has completed
+    IWB_CUDA(cudaStreamSynchronize(st));
+    return enqueue_slab(h, c, p, table_device, st, p->rho_out);
+}
+
+int iwb_reduce_table(iwb_handle* h, const double* table_device, int nrows, int nshell, void* stream, iwb_result* out)
+{
+    if (!h || !table_device || !out || nrows < 1) return fail(IWB_ERR_INVALID, "iwb_reduce_table: bad argument");
+    IWB_CUDA(cudaSetDevice(h->device));
+    Scratch& c = h->scr[0];
+    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    IWB_CUDA(c.out.reserve(ROW_BYTES_MIN));
+    IWB_CUDA(c.h_out.reserve(ROW_BYTES_MIN));
+    k_reduce_rows<<<1, 128, 0, st>>>(table_device, (double*)c.out.p, nrows);
+    IWB_CUDA(cudaGetLastError());
+    IWB_CUDA(cudaMemcpyAsync(c.h_out.p, c.out.p, ROW_BYTES_MIN, cudaMemcpyDeviceToHost, st));
+    IWB_CUDA(cudaStreamSynchronize(st));
+    memset(out, 0, sizeof(*out));
+    unpack_row((const double*)c.h_out.p, nshell, out);
+    return IWB_OK;
+}
+
+int iwb_energy3d_batch(iwb_handle* h, int npoints, const iwb_params3d* pts, iwb_result* outs)
+{
+    if (!h || npoints < 0 || (npoints > 0 && (!pts || !outs))) return fail(IWB_ERR_INVALID, "iwb_energy3d_batch: bad argument");
+    for (int q = 0; q < npoints; ++q) {
+        int rc = validate(&pts[q]);
+        if (rc) return rc;
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    IWB_CUDA(cudaSetDevice(h->device));
+    // NSCRATCH evaluations in flight; a scratch is recycled after its previous occupant completed
+    for (int base = 0; base < npoints; base += NSCRATCH) {
+        const int m = (npoints - base < NSCRATCH) ? npoints - base : NSCRATCH;
+        for (int q = 0; q < m; ++q) {
+            int rc = enqueue_full(h, h->scr[q], &pts[base + q]);
+            if (rc) return rc;
+        }
+        for (int q = 0; q < m; ++q) {
+            Scratch& c = h->scr[q];
+            IWB_CUDA(cudaStreamSynchronize(c.stream));
+            memset(&outs[base + q], 0, sizeof(iwb_result));
+            unpack_row((const double*)c.h_out.p, pts[base + q].nshell, &outs[base + q]);
+            float ms = 0;
+            IWB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+            outs[base + q].kernel_ms = ms;
+        }
+    }
+    const double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (int q = 0; q < npoints; ++q) outs[q].total_ms = total;
+    return IWB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// Host-side plumbing shared by the C-ABI translation units (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/iwb200.h"
+#include "iwb_device.cuh"
+
+namespace iwb {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define IWB_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t err__ = (call);                                                            \
+        if (err__ != cudaSuccess)                                                              \
+            return ::iwb::fail(IWB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__)); \
+    } while (0)
+
+// grow-only device / pinned-host buffers
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// One in-flight evaluation's worth of scratch (a batch uses several, round-robin).
+struct Scratch {
+    cudaStream_t stream = nullptr;
+    DevBuf coords;     // x, xx, yy, zz
+    DevBuf partial;    // [nfb][ntiles][ROW]
+    DevBuf table;      // [nfb][ROW]
+    DevBuf out;        // [ROW]
+    DevBuf rho;        // staging for a host rho_out
+    PinBuf h_coords;
+    PinBuf h_out;      // [ROW]
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+constexpr int NSCRATCH = 4;
+constexpr size_t ROW_BYTES_MIN = IWB_ROW_WIDTH * sizeof(double);
+
+}  // namespace iwb
+
+struct iwb_handle {
+    int device = -1;
+    int sm_count = 0;
+    cudaDeviceProp prop;
+    iwb::Scratch scr[iwb::NSCRATCH];
+    int k3_config = 0;         // kernel geometry variant (IWB_K3_CONFIG env override)
+    int k3_seg_len = 0;        // planes per work item override (0 = heuristic)
+};
+
+namespace iwb {
+AxisCoef make_axis_coef(double h);
+double shell_threshold_f64(double R);
+double shell_threshold_f32(double R);
+PhiConst make_phi_const(double rho, double sigma, double v, double eps, double sinh_rs, double cosh_rs);
+}  // namespace iwb

@@ -1,0 +1,193 @@
+"""Process-wide engine handle (one CUDA device per process) and thin typed wrappers.
+
+Replaces the role of ``_resolve_backend`` (/root/reference/scripts/reproduce_rodal_exact.py:16-30)
+for ``backend="b200"``: instead of returning an array module it hands out the handle the
+fused evaluators run on.  Creation fails loudly (RuntimeError) without a usable GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import _capi
+
+_lock = threading.Lock()
+_engines: dict[int, "Engine"] = {}
+
+
+def _as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Engine:
+    """Owns one ``iwb_handle`` (streams, scratch) on one device."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _capi.load()
+        h = C.c_void_p()
+        _capi.check(self._lib.iwb_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        sm, major, minor = C.c_int(), C.c_int(), C.c_int()
+        name = C.create_string_buffer(128)
+        _capi.check(self._lib.iwb_device_info(h, C.byref(sm), C.byref(major), C.byref(minor), name, 128))
+        self.sm_count = sm.value
+        self.cc = (major.value, minor.value)
+        self.name = name.value.decode()
+
+    def close(self):
+        if self._h:
+            self._lib.iwb_destroy(self._h)
+            self._h = None
+
+    # -- 3D ---------------------------------------------------------------------------------
+    @staticmethod
+    def make_params3d(*, x, y, z, dx, dy, dz, rho, sigma, v, dtype, shells=(), eps=1e-12,
+                      i_begin=0, i_end=None, rho_out=None, rho_out_is_device=False):
+        """Fill an ``iwb_params3d``.  ``x, y, z`` are the host linspace arrays (float32 grids are
+        widened to float64 without change of value).  Returns (params, keepalive)."""
+        xd, yd, zd = _as_f64(x), _as_f64(y), _as_f64(z)
+        shells = [float(s) for s in shells]
+        if len(shells) > _capi.MAX_SHELLS:
+            raise ValueError(f"at most {_capi.MAX_SHELLS} shell radii per call")
+        p = _capi.Params3D()
+        p.dtype = _capi.F32_REF if dtype == "float32" else _capi.F64
+        p.mode = _capi.MODE_EXACT
+        p.n0, p.n1, p.n2 = len(xd), len(yd), len(zd)
+        p.i_begin = int(i_begin)
+        p.i_end = len(xd) if i_end is None else int(i_end)
+        p.x, p.y, p.z = _ptr(xd), _ptr(yd), _ptr(zd)
+        p.dx, p.dy, p.dz = float(dx), float(dy), float(dz)
+        p.rho, p.sigma, p.v, p.eps = float(rho), float(sigma), float(v), float(eps)
+        rs = rho * sigma                       # potential.py:50-52: np.sinh / np.cosh of a Python float
+        p.sinh_rs, p.cosh_rs = float(np.sinh(rs)), float(np.cosh(rs))
+        p.nshell = len(shells)
+        for s, r in enumerate(shells):
+            p.shell_r[s] = r
+        keep = [xd, yd, zd]
+        if rho_out is not None:
+            if rho_out_is_device:
+                p.rho_out = int(rho_out)
+                p.rho_out_is_device = 1
+            else:
+                assert rho_out.dtype == np.float64 and rho_out.flags.c_contiguous
+                p.rho_out = rho_out.ctypes.data
+                keep.append(rho_out)
+        return p, keep
+
+    @staticmethod
+    def _result_dict(r, nshell):
+        return {
+            "e_pos": r.e_pos, "e_neg": r.e_neg,
+            "cnt_pos": r.cnt_pos, "cnt_neg": r.cnt_neg, "cnt_zero": r.cnt_zero, "cnt_nan": r.cnt_nan,
+            "shell_pos": [r.shell_pos[s] for s in range(nshell)],
+            "shell_neg": [r.shell_neg[s] for s in range(nshell)],
+            "shell_cnt": [r.shell_cnt[s] for s in range(nshell)],
+            "kernel_ms": r.kernel_ms, "total_ms": r.total_ms,
+        }
+
+    def energy3d(self, **kw):
+        p, keep = self.make_params3d(**kw)
+        r = _capi.Result()
+        _capi.check(self._lib.iwb_energy3d(self._h, C.byref(p), C.byref(r)))
+        del keep
+        return self._result_dict(r, p.nshell)
+
+    def energy3d_batch(self, points):
+        """``points``: list of kwargs for :meth:`make_params3d`; one host sync for the whole batch."""
+        n = len(points)
+        arr = (_capi.Params3D * n)()
+        keep = []
+        for q, kw in enumerate(points):
+            p, k = self.make_params3d(**kw)
+            arr[q] = p
+            keep.append(k)
+        res = (_capi.Result * n)()
+        _capi.check(self._lib.iwb_energy3d_batch(self._h, n, arr, res))
+        del keep
+        return [self._result_dict(res[q], arr[q].nshell) for q in range(n)]
+
+    def energy3d_slab_async(self, table_ptr, stream_ptr=None, **kw):
+        p, keep = self.make_params3d(**kw)
+        _capi.check(self._lib.iwb_energy3d_slab_async(self._h, C.byref(p), C.c_void_p(int(table_ptr)),
+                                                      C.c_void_p(int(stream_ptr or 0))))
+        return keep
+
+    def reduce_table(self, table_ptr, nrows, nshell, stream_ptr=None):
+        r = _capi.Result()
+        _capi.check(self._lib.iwb_reduce_table(self._h, C.c_void_p(int(table_ptr)), int(nrows), int(nshell),
+                                               C.c_void_p(int(stream_ptr or 0)), C.byref(r)))
+        return self._result_dict(r, nshell)
+
+    # -- axisymmetric ---------------------------------------------------------------------------
+    def energy_axisym(self, *, x, y, dx, dy, rho, sigma, v, dtype, shells=(), eps=1e-12, rho_out=None):
+        xd, yd = _as_f64(x), _as_f64(y)
+        shells = [float(s) for s in shells]
+        if len(shells) > _capi.MAX_SHELLS:
+            raise ValueError(f"at most {_capi.MAX_SHELLS} shell radii per call")
+        p = _capi.ParamsAxisym()
+        p.dtype = _capi.F32_REF if dtype == "float32" else _capi.F64
+        p.mode = _capi.MODE_EXACT
+        p.nx, p.ny = len(xd), len(yd)
+        p.x, p.y = _ptr(xd), _ptr(yd)
+        p.dx, p.dy = float(dx), float(dy)
+        p.rho, p.sigma, p.v, p.eps = float(rho), float(sigma), float(v), float(eps)
+        rs = rho * sigma
+        p.sinh_rs, p.cosh_rs = float(np.sinh(rs)), float(np.cosh(rs))
+        p.nshell = len(shells)
+        for s, r in enumerate(shells):
+            p.shell_r[s] = r
+        if rho_out is not None:
+            assert rho_out.dtype == np.float64 and rho_out.flags.c_contiguous and rho_out.shape == (len(yd), len(xd))
+            p.rho_out = _ptr(rho_out)
+        r = _capi.Result()
+        _capi.check(self._lib.iwb_energy_axisym(self._h, C.byref(p), C.byref(r)))
+        return self._result_dict(r, p.nshell)
+
+    # -- 2D slice -----------------------------------------------------------------------------------
+    def slice_z0(self, *, x, y, dx, dy, rho, sigma, v, eps=1e-12):
+        xd, yd = _as_f64(x), _as_f64(y)
+        n = len(xd)
+        if len(yd) != n:
+            raise ValueError("slice_z0 needs a square grid")
+        fields = {k: np.empty((n, n), dtype=np.float64) for k in ("phi", "beta_x", "beta_y", "rho_adm")}
+        p = _capi.ParamsSlice()
+        p.n = n
+        p.x, p.y = _ptr(xd), _ptr(yd)
+        p.dx, p.dy = float(dx), float(dy)
+        p.rho, p.sigma, p.v, p.eps = float(rho), float(sigma), float(v), float(eps)
+        p.phi, p.beta_x, p.beta_y, p.rho_adm = (_ptr(fields[k]) for k in ("phi", "beta_x", "beta_y", "rho_adm"))
+        r = _capi.SliceResultC()
+        _capi.check(self._lib.iwb_slice_z0(self._h, C.byref(p), C.byref(r)))
+        fields.update(pos=r.pos, neg=r.neg, net=r.net, cnt_pos=r.cnt_pos, cnt_neg=r.cnt_neg,
+                      cnt_zero=r.cnt_zero, kernel_ms=r.kernel_ms, total_ms=r.total_ms)
+        return fields
+
+    # -- diagnostics ----------------------------------------------------------------------------
+    def measure_fma_peak(self, fp32=False):
+        t, mhz = C.c_double(), C.c_double()
+        _capi.check(self._lib.iwb_measure_fma_peak(self._h, 1 if fp32 else 0, C.byref(t), C.byref(mhz)))
+        return {"tflops": t.value, "sm_mhz_effective": mhz.value}
+
+    def selftest_constdiv(self, divisor, count=1 << 26, seed=1):
+        bad = C.c_uint64()
+        _capi.check(self._lib.iwb_selftest_constdiv(self._h, float(divisor), int(count), int(seed), C.byref(bad)))
+        return bad.value
+
+
+def get_engine(device: int | None = None) -> Engine:
+    """The engine of this process (device = LOCAL_RANK under torchrun, else 0)."""
+    if device is None:
+        device = int(os.environ.get("IWB_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _lock:
+        eng = _engines.get(device)
+        if eng is None:
+            eng = _engines[device] = Engine(device)
+        return eng
