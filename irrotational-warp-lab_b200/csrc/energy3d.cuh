@@ -134,7 +134,6 @@ k_energy3d(const __grid_constant__ K3Params P)
             const double* const ph_m2 = phi_ring + ((p + 1) % 3) * PLANE;   // plane p-2
             const bool do_px = (p - 2 >= pstart);            // phi_x(p-1), interior formula
             const bool do_px0 = (p == 2) && (pstart == 0);   // phi_x(0), one-sided
-            const bool do_pxn = (p == P.n0 - 1);             // phi_x(n0-1), one-sided
 #pragma unroll
             for (int bb = 0; bb < NB; bb += 2) {
                 double f[4];
@@ -156,8 +155,23 @@ k_energy3d(const __grid_constant__ K3Params P)
                     ph_p[idx] = f[q];
                     if (do_px) px_ring[((p + 2) % 3) * PLANE + idx] = cdiv(f[q] - ph_m2[idx], cx.h2, cx.rh2);
                     if (do_px0) px_ring[idx] = edge3(cx.a0, ph_m2[idx], cx.b0, ph_m1[idx], cx.c0, f[q]);
-                    if (do_pxn)   // phi(n0-3) is plane p-2
-                        px_ring[(p % 3) * PLANE + idx] = edge3(cx.a1, ph_m2[idx], cx.b1, ph_m1[idx], cx.c1, f[q]);
+                }
+            }
+        };
+
+        // ---- phi_x(n0-1), one-sided.  Its ring slot still holds phi_x(n0-4) until plane n0-3 has been
+        //      output, so it is computed separately, once the march reaches plane n0-2 (or at once if n0 == 3).
+        auto produce_px_last = [&]() {
+            const int p = P.n0 - 1;
+            const double* const ph_p = phi_ring + (p % 3) * PLANE;
+            const double* const ph_m1 = phi_ring + ((p + 2) % 3) * PLANE;
+            const double* const ph_m2 = phi_ring + ((p + 1) % 3) * PLANE;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const int idx = jr_[b] * RK + tx + 32 * a;
+                    px_ring[(p % 3) * PLANE + idx] = edge3(cx.a1, ph_m2[idx], cx.b1, ph_m1[idx], cx.c1, ph_p[idx]);
                 }
             }
         };
@@ -327,6 +341,7 @@ k_energy3d(const __grid_constant__ K3Params P)
         // ---- march ------------------------------------------------------------------------
         __syncthreads();                 // previous item's shared memory is dead
         int produced = pstart - 1;
+        bool px_last_done = false;
         for (int i = i0; i < i1; ++i) {
             const int target = min(max(i + 2, 3), P.n0 - 1);
             const int early = min(target, i + 2);
@@ -336,6 +351,10 @@ k_energy3d(const __grid_constant__ K3Params P)
             if (produced < target) {                 // only i == 0: phi(3) reuses the slot of phi(0)
                 __syncthreads();
                 produce(++produced);
+            }
+            if (!px_last_done && max(i - 1, 0) >= P.n0 - 3 && produced == P.n0 - 1) {
+                produce_px_last();
+                px_last_done = true;
             }
             __syncthreads();
             output(i);
