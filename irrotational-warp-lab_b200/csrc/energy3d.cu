@@ -15,16 +15,20 @@
 namespace iwb {
 
 // ---- kernel geometry variants -----------------------------------------------------------------
-//   config 0: region 32 x 64, 8 warps, 128 KB smem, 1 CTA / SM
-//   config 1: region 24 x 64, 6 warps,  96 KB smem, 2 CTAs / SM
+//   config 0: region 32 x 64, 16 warps, 1 CTA / SM (default)
+//   config 1: region 48 x 64, 16 warps, 1 CTA / SM
+//   config 2: region 24 x 64,  8 warps, 2 CTAs / SM
+//   config 3: region 40 x 64, 20 warps, 1 CTA / SM
+// Only the headline variant (float64, <= 2 shells, no rho emission) is built for the experimental
+// configs; every other variant uses config 0.
 struct K3Config { int rj, nw; };
-static const K3Config kConfigs[] = {{32, 8}, {24, 6}};
-constexpr int kNumConfigs = 2;
+static const K3Config kConfigs[] = {{32, 16}, {48, 16}, {24, 8}, {40, 20}};
+constexpr int kNumConfigs = 4;
 
-template <int DT, int NSH, int RJ, int NW, bool EMIT>
+template <int DT, int NSH, int RJ, int NW, bool EMIT, int MINB>
 static cudaError_t launch_one(const K3Params& P, int sm_count, cudaStream_t st)
 {
-    auto kern = k_energy3d<DT, NSH, RJ, NW, EMIT>;
+    auto kern = k_energy3d<DT, NSH, RJ, NW, EMIT, MINB>;
     constexpr size_t smem = Geo<RJ, NW>::SMEM_BYTES;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -38,13 +42,24 @@ static cudaError_t launch_one(const K3Params& P, int sm_count, cudaStream_t st)
     return cudaGetLastError();
 }
 
+static bool config_is_built(int cfg, int dtype, int nshell, bool emit)
+{
+    if (cfg == 0) return true;
+    return cfg > 0 && cfg < kNumConfigs && dtype == IWB_F64 && nshell <= 2 && !emit;
+}
+
 template <int DT, int NSH, bool EMIT>
 static cudaError_t launch_cfg(int cfg, const K3Params& P, int sm_count, cudaStream_t st)
 {
-    switch (cfg) {
-    case 1: return launch_one<DT, NSH, 24, 6, EMIT>(P, sm_count, st);
-    default: return launch_one<DT, NSH, 32, 8, EMIT>(P, sm_count, st);
+    if (DT == IWB_F64 && NSH == 2 && !EMIT) {
+        switch (cfg) {
+        case 1: return launch_one<IWB_F64, 2, 48, 16, false, 1>(P, sm_count, st);
+        case 2: return launch_one<IWB_F64, 2, 24, 8, false, 2>(P, sm_count, st);
+        case 3: return launch_one<IWB_F64, 2, 40, 20, false, 1>(P, sm_count, st);
+        default: break;
+        }
     }
+    return launch_one<DT, NSH, 32, 16, EMIT, 1>(P, sm_count, st);
 }
 
 template <int DT, bool EMIT>
@@ -88,8 +103,8 @@ static int enqueue_slab(iwb_handle* h, Scratch& c, const iwb_params3d* p, double
                         double* rho_dev)
 {
     const int n0 = p->n0, n1 = p->n1, n2 = p->n2;
-    const K3Config cfg = kConfigs[(h->k3_config >= 0 && h->k3_config < kNumConfigs) ? h->k3_config : 0];
-    const int cfg_id = (h->k3_config >= 0 && h->k3_config < kNumConfigs) ? h->k3_config : 0;
+    const int cfg_id = config_is_built(h->k3_config, p->dtype, p->nshell, rho_dev != nullptr) ? h->k3_config : 0;
+    const K3Config cfg = kConfigs[cfg_id];
 
     // coordinates: x, x*x, y*y, z*z (squares rounded once in the coordinate dtype, as x*x is in NumPy)
     const size_t ncoord = (size_t)2 * n0 + n1 + n2;

@@ -8,14 +8,17 @@
 // Decomposition.  The volume is C-order [i, j, k] (k contiguous).  A work item is
 // (tile of the (j, k) plane) x (range of i planes); the CTA marches along i.
 // The CTA's region is the tile plus a 2-point halo: RJ rows (j) x 64 columns (k),
-// lanes along k.  Thread (tx, ty) owns region columns (jr = ty + NW*b, kr = tx + 32*a).
+// lanes along k.  Warp w owns region rows jr = w, w+NW, ...; lane tx owns columns tx, tx+32.
 //
 // Shared memory (doubles, RJ x 64 each):   phi ring [3]   planes p-2, p-1, p
 //                                           phi_x ring [3] planes of d(phi)/dx
 //                                           phi_y, phi_z   of the current output plane
-// Per output plane i:   produce phi(i+2) and phi_x(i+1) (own columns only),
-//                       phi_y(i), phi_z(i) from the phi(i) plane   | __syncthreads
-//                       second derivatives, rho, predicated sums    | __syncthreads
+// Per output plane i:   phase 1: phi(i+2), phi_x(i+1) (own columns) and phi_y(i), phi_z(i)
+//                                from the phi(i) plane                      | __syncthreads
+//                       phase 2: second derivatives, rho, predicated sums   | __syncthreads
+// The row loops are deliberately NOT unrolled (two columns of ILP per thread, 16 warps per SM
+// for latency hiding): the IEEE division / sqrt sequences are long and an unrolled body
+// overflows the instruction cache.
 // Sums are kept in registers and flushed (warp shuffle + fixed-order block tree) once
 // per IWB_FLUSH_PLANES planes into partial[flush block][tile][row]; a second kernel adds
 // the tiles in fixed order.  Flush blocks are aligned to the GLOBAL plane index, so the
@@ -30,6 +33,7 @@ constexpr int RK = 64;              // region columns (k): two per lane
 constexpr int TK_MAX = RK - 4;      // tile columns
 constexpr int ROW = IWB_ROW_WIDTH;  // doubles per partial row
 constexpr int FLUSH = IWB_FLUSH_PLANES;
+constexpr int SMEM_PAD = 2 * RK;    // guard doubles before and after the planes (halo reads of edge lanes)
 
 struct K3Params {
     int n0, n1, n2;
@@ -49,38 +53,35 @@ struct K3Params {
     double* rho_out;               // NULL or [i_end-i_begin][n1][n2]
 };
 
-// region geometry helpers
 __host__ __device__ inline int tile_begin(int t, int nt, int n) { return (int)(((long long)t * n) / nt); }
 
 template <int RJ, int NW>
 struct Geo {
-    static constexpr int NB = RJ / NW;          // rows per thread
-    static constexpr int NC = NB * 2;           // columns per thread
     static constexpr int PLANE = RJ * RK;
     static constexpr int TJ_MAX = RJ - 4;
     static constexpr int NT = NW * 32;
-    static constexpr size_t SMEM_BYTES = size_t(8) * PLANE * sizeof(double);
-    static_assert(RJ % NW == 0, "rows must divide among warps");
-    static_assert(NB % 2 == 0, "phi is evaluated in batches of 2 rows x 2 columns");
+    static constexpr size_t SMEM_BYTES = (size_t(8) * PLANE + 2 * SMEM_PAD + RJ) * sizeof(double);
 };
 
-template <int DT, int NSH, int RJ, int NW, bool EMIT>
-__global__ void __launch_bounds__(NW * 32, (Geo<RJ, NW>::SMEM_BYTES <= 112 * 1024) ? 2 : 1)
+template <int DT, int NSH, int RJ, int NW, bool EMIT, int MINB = 1>
+__global__ void __launch_bounds__(NW * 32, MINB)
 k_energy3d(const __grid_constant__ K3Params P)
 {
     using G = Geo<RJ, NW>;
-    constexpr int NB = G::NB;
     constexpr int PLANE = G::PLANE;
-    extern __shared__ double smem[];
-    double* const phi_ring = smem;
-    double* const px_ring = smem + 3 * PLANE;
-    double* const py_buf = smem + 6 * PLANE;
-    double* const pz_buf = smem + 7 * PLANE;
+    constexpr int NSHA = NSH > 0 ? NSH : 1;
+    extern __shared__ double smem_raw[];
+    double* const phi_ring = smem_raw + SMEM_PAD;
+    double* const px_ring = phi_ring + 3 * PLANE;
+    double* const py_buf = phi_ring + 6 * PLANE;
+    double* const pz_buf = phi_ring + 7 * PLANE;
+    double* const yy_s = phi_ring + 8 * PLANE + SMEM_PAD;   // [RJ] y*y of the region rows
 
     const int tx = threadIdx.x & 31;
     const int ty = threadIdx.x >> 5;
     const int ntiles = P.ntj * P.ntk;
     const AxisCoef cx = P.cx, cy = P.cy, cz = P.cz;
+    const PhiConst pc = P.pc;
 
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
         const int seg = item / ntiles;
@@ -91,70 +92,109 @@ k_energy3d(const __grid_constant__ K3Params P)
         const int i0 = P.i_begin + seg * P.seg_len;
         const int i1 = min(P.i_end, i0 + P.seg_len);
 
-        // ---- loop-invariant description of this thread's columns -------------------
-        double yyv[NB], zzv[2];
-        int jr_[NB];
-        unsigned rowf[NB];   // bit0 valid, bit1 j==0, bit2 j==n1-1, bit3 wants phi_y/phi_z, bit4 output row
-        unsigned colf[2];    // same for k
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            int jr = ty + NW * b, j = j0 - 2 + jr;
-            bool valid = (j >= 0) && (j < P.n1) && (jr < Tj + 4);
-            jr_[b] = jr;
-            yyv[b] = P.yy[min(max(j, 0), P.n1 - 1)];
-            rowf[b] = (valid ? 1u : 0u) | ((j == 0) ? 2u : 0u) | ((j == P.n1 - 1) ? 4u : 0u) |
-                      ((valid && jr >= 1 && jr <= Tj + 2) ? 8u : 0u) |
-                      ((jr >= 2 && jr <= Tj + 1) ? 16u : 0u);
-        }
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            int kr = tx + 32 * a, k = k0 - 2 + kr;
-            bool valid = (k >= 0) && (k < P.n2) && (kr < Tk + 4);
-            zzv[a] = P.zz[min(max(k, 0), P.n2 - 1)];
-            colf[a] = (valid ? 1u : 0u) | ((k == 0) ? 2u : 0u) | ((k == P.n2 - 1) ? 4u : 0u) |
-                      ((valid && kr >= 1 && kr <= Tk + 2) ? 8u : 0u) |
-                      ((kr >= 2 && kr <= Tk + 1) ? 16u : 0u);
+        // region rows [jr_lo, jr_hi] exist in the grid; j == 0 is region row 2 of a low-edge tile,
+        // j == n1-1 is region row Tj+1 of a high-edge tile
+        const bool t_jlo = (j0 == 0), t_jhi = (j0 + Tj == P.n1);
+        const bool t_kedge = (k0 == 0) || (k0 + Tk == P.n2);
+        const int jr_lo = t_jlo ? 2 : 0, jr_hi = t_jhi ? Tj + 1 : Tj + 3;
+        const int py_lo = max(jr_lo, 1), py_hi = min(jr_hi, Tj + 2);
+
+        __syncthreads();                 // previous item's shared memory is dead
+        if (threadIdx.x < RJ) yy_s[threadIdx.x] = P.yy[min(max(j0 - 2 + (int)threadIdx.x, 0), P.n1 - 1)];
+
+        // this lane's two columns
+        double zz0, zz1;
+        unsigned cf0, cf1;       // bit1 k==0, bit2 k==n2-1, bit4 output column
+        {
+            const int ka = k0 - 2 + tx, kb = ka + 32;
+            zz0 = P.zz[min(max(ka, 0), P.n2 - 1)];
+            zz1 = P.zz[min(max(kb, 0), P.n2 - 1)];
+            cf0 = ((ka == 0) ? 2u : 0u) | ((ka == P.n2 - 1) ? 4u : 0u) | ((tx >= 2 && tx <= Tk + 1) ? 16u : 0u);
+            cf1 = ((kb == 0) ? 2u : 0u) | ((kb == P.n2 - 1) ? 4u : 0u) | ((tx + 32 <= Tk + 1) ? 16u : 0u);
         }
 
         // ---- accumulators (registers) -------------------------------------------------
         double acc_pos = 0.0, acc_neg = 0.0;
-        double sh_pos[NSH > 0 ? NSH : 1], sh_neg[NSH > 0 ? NSH : 1];
+        double sh_pos[NSHA], sh_neg[NSHA];
         int c_pos = 0, c_neg = 0, c_zero = 0, c_nan = 0;
-        int sh_cnt[NSH > 0 ? NSH : 1];
+        int sh_cnt[NSHA];
 #pragma unroll
-        for (int s = 0; s < NSH; ++s) { sh_pos[s] = 0.0; sh_neg[s] = 0.0; sh_cnt[s] = 0; }
+        for (int s = 0; s < NSHA; ++s) { sh_pos[s] = 0.0; sh_neg[s] = 0.0; sh_cnt[s] = 0; }
 
-        // ---- produce plane p: phi(p) and the x-derivatives it completes -----------------
         const int w0 = min(max(i0 - 1, 0), P.n0 - 3);
         const int pstart = max(0, w0 - 1);
-        auto produce = [&](int p) {
-            const double xp = P.x[p], xxp = P.xx[p];
-            double* const ph_p = phi_ring + (p % 3) * PLANE;
-            const double* const ph_m1 = phi_ring + ((p + 2) % 3) * PLANE;   // plane p-1
-            const double* const ph_m2 = phi_ring + ((p + 1) % 3) * PLANE;   // plane p-2
-            const bool do_px = (p - 2 >= pstart);            // phi_x(p-1), interior formula
-            const bool do_px0 = (p == 2) && (pstart == 0);   // phi_x(0), one-sided
-#pragma unroll
-            for (int bb = 0; bb < NB; bb += 2) {
-                double f[4];
-                if (DT == IWB_F64) {
-                    double s[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) s[q] = (xxp + yyv[bb + (q >> 1)]) + zzv[q & 1];
-                    phi_exact_f64<4>(s, xp, P.pc, f);
-                } else {
-                    float s[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        s[q] = __fadd_rn(__fadd_rn((float)xxp, (float)yyv[bb + (q >> 1)]), (float)zzv[q & 1]);
-                    phi_exact_f32ref<4>(s, (float)xp, P.pc, f);
+
+        // d/dz (along lanes) of a staged plane; one-sided at the global faces
+        auto dZ = [&](const double* B, int idx, unsigned cf) -> double {
+            double d = cdiv(B[idx + 1] - B[idx - 1], cz.h2, cz.rh2);
+            if (t_kedge) {
+                if (cf & 2u) d = edge3(cz.a0, B[idx], cz.b0, B[idx + 1], cz.c0, B[idx + 2]);
+                else if (cf & 4u) d = edge3(cz.a1, B[idx - 2], cz.b1, B[idx - 1], cz.c1, B[idx]);
+            }
+            return d;
+        };
+        // d/dy (along rows); jedge: 0 interior, 1 row j == 0, 2 row j == n1-1 (warp-uniform)
+        auto dY = [&](const double* B, int idx, int jedge) -> double {
+            if (jedge == 1) return edge3(cy.a0, B[idx], cy.b0, B[idx + RK], cy.c0, B[idx + 2 * RK]);
+            if (jedge == 2) return edge3(cy.a1, B[idx - 2 * RK], cy.b1, B[idx - RK], cy.c1, B[idx]);
+            return cdiv(B[idx + RK] - B[idx - RK], cy.h2, cy.rh2);
+        };
+
+        // ---- phase 1 -----------------------------------------------------------------------
+        // p >= 0: produce phi(p) and the x-derivative it completes (own columns only).
+        // ip >= 0: phi_y(ip), phi_z(ip) from the phi(ip) plane (reads neighbours' columns).
+        auto phase1 = [&](int p, int ip) {
+            double xp = 0.0, xxp = 0.0;
+            double* ph_p = phi_ring;
+            const double *ph_m1 = phi_ring, *ph_m2 = phi_ring;
+            double* px_w = px_ring;
+            bool do_px = false, do_px0 = false;
+            if (p >= 0) {
+                xp = P.x[p]; xxp = P.xx[p];
+                ph_p = phi_ring + (p % 3) * PLANE;
+                ph_m1 = phi_ring + ((p + 2) % 3) * PLANE;      // plane p-1
+                ph_m2 = phi_ring + ((p + 1) % 3) * PLANE;      // plane p-2
+                px_w = px_ring + ((p + 2) % 3) * PLANE;        // phi_x(p-1)
+                do_px = (p - 2 >= pstart);                     // interior formula
+                do_px0 = (p == 2) && (pstart == 0);            // phi_x(0), one-sided
+            }
+            const double* const ph_i = phi_ring + ((ip >= 0 ? ip : 0) % 3) * PLANE;
+#pragma unroll 1
+            for (int jr = ty; jr <= jr_hi; jr += NW) {
+                if (jr < jr_lo) continue;
+                const int base = jr * RK + tx;
+                if (p >= 0) {
+                    double f[2];
+                    if (DT == IWB_F64) {
+                        const double sxy = xxp + yy_s[jr];
+                        const double s[2] = {sxy + zz0, sxy + zz1};
+                        phi_exact_f64<2>(s, xp, pc, f);
+                    } else {
+                        const float sxy = __fadd_rn((float)xxp, (float)yy_s[jr]);
+                        const float s[2] = {__fadd_rn(sxy, (float)zz0), __fadd_rn(sxy, (float)zz1)};
+                        phi_exact_f32ref<2>(s, (float)xp, pc, f);
+                    }
+                    ph_p[base] = f[0];
+                    ph_p[base + 32] = f[1];
+                    if (do_px) {
+                        px_w[base] = cdiv(f[0] - ph_m2[base], cx.h2, cx.rh2);
+                        px_w[base + 32] = cdiv(f[1] - ph_m2[base + 32], cx.h2, cx.rh2);
+                    }
+                    if (do_px0) {
+                        px_ring[base] = edge3(cx.a0, ph_m2[base], cx.b0, ph_m1[base], cx.c0, f[0]);
+                        px_ring[base + 32] = edge3(cx.a0, ph_m2[base + 32], cx.b0, ph_m1[base + 32], cx.c0, f[1]);
+                    }
                 }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int idx = jr_[bb + (q >> 1)] * RK + tx + 32 * (q & 1);
-                    ph_p[idx] = f[q];
-                    if (do_px) px_ring[((p + 2) % 3) * PLANE + idx] = cdiv(f[q] - ph_m2[idx], cx.h2, cx.rh2);
-                    if (do_px0) px_ring[idx] = edge3(cx.a0, ph_m2[idx], cx.b0, ph_m1[idx], cx.c0, f[q]);
+                if (ip >= 0) {
+                    if (jr >= py_lo && jr <= py_hi) {
+                        const int jedge = (t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0);
+                        py_buf[base] = dY(ph_i, base, jedge);
+                        py_buf[base + 32] = dY(ph_i, base + 32, jedge);
+                    }
+                    if (jr >= 2 && jr <= Tj + 1) {
+                        pz_buf[base] = dZ(ph_i, base, cf0);
+                        pz_buf[base + 32] = dZ(ph_i, base + 32, cf1);
+                    }
                 }
             }
         };
@@ -166,116 +206,87 @@ k_energy3d(const __grid_constant__ K3Params P)
             const double* const ph_p = phi_ring + (p % 3) * PLANE;
             const double* const ph_m1 = phi_ring + ((p + 2) % 3) * PLANE;
             const double* const ph_m2 = phi_ring + ((p + 1) % 3) * PLANE;
+            double* const px_w = px_ring + (p % 3) * PLANE;
+#pragma unroll 1
+            for (int jr = ty; jr <= jr_hi; jr += NW) {
+                if (jr < jr_lo) continue;
+                const int base = jr * RK + tx;
+                px_w[base] = edge3(cx.a1, ph_m2[base], cx.b1, ph_m1[base], cx.c1, ph_p[base]);
+                px_w[base + 32] = edge3(cx.a1, ph_m2[base + 32], cx.b1, ph_m1[base + 32], cx.c1, ph_p[base + 32]);
+            }
+        };
+
+        // ---- predicated sums of one point (reproduce_rodal_exact.py:57-61, 220-224) ----------
+        auto tally = [&](double e, bool out_col, double yyj, double zzk, double xxi) {
+            const bool pos = out_col && (e > 0.0), neg = out_col && (e < 0.0);
+            acc_pos += pos ? e : 0.0;
+            acc_neg += neg ? e : 0.0;
+            c_pos += pos; c_neg += neg;
+            c_zero += (out_col && e == 0.0); c_nan += (out_col && e != e);
+            if (NSH > 0) {
+                bool in_[NSHA];
+                if (DT == IWB_F64) {
+                    const double s = (xxi + yyj) + zzk;
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
+                    for (int sh = 0; sh < NSH; ++sh) in_[sh] = out_col && (s <= P.shell_thr[sh]);
+                } else {
+                    const float s = __fadd_rn(__fadd_rn((float)xxi, (float)yyj), (float)zzk);
 #pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const int idx = jr_[b] * RK + tx + 32 * a;
-                    px_ring[(p % 3) * PLANE + idx] = edge3(cx.a1, ph_m2[idx], cx.b1, ph_m1[idx], cx.c1, ph_p[idx]);
+                    for (int sh = 0; sh < NSH; ++sh) in_[sh] = out_col && (s <= (float)P.shell_thr[sh]);
+                }
+#pragma unroll
+                for (int sh = 0; sh < NSH; ++sh) {
+                    sh_pos[sh] += (in_[sh] && pos) ? e : 0.0;
+                    sh_neg[sh] += (in_[sh] && neg) ? e : 0.0;
+                    sh_cnt[sh] += in_[sh];
                 }
             }
         };
 
-        // ---- phi_y(i), phi_z(i) of the own columns from the phi(i) plane ------------------
-        auto inplane = [&](int i) {
-            const double* const ph = phi_ring + (i % 3) * PLANE;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const int jr = jr_[b];
-                const bool row_ok = (rowf[b] & 8u) != 0;
-#pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const int kr = tx + 32 * a;
-                    const int idx = jr * RK + kr;
-                    if (row_ok && (colf[a] & 1u)) {
-                        double d;
-                        if (rowf[b] & 2u) d = edge3(cy.a0, ph[idx], cy.b0, ph[idx + RK], cy.c0, ph[idx + 2 * RK]);
-                        else if (rowf[b] & 4u) d = edge3(cy.a1, ph[idx - 2 * RK], cy.b1, ph[idx - RK], cy.c1, ph[idx]);
-                        else d = cdiv(ph[idx + RK] - ph[idx - RK], cy.h2, cy.rh2);
-                        py_buf[idx] = d;
-                    }
-                    if ((rowf[b] & 1u) && (colf[a] & 8u)) {
-                        double d;
-                        if (colf[a] & 2u) d = edge3(cz.a0, ph[idx], cz.b0, ph[idx + 1], cz.c0, ph[idx + 2]);
-                        else if (colf[a] & 4u) d = edge3(cz.a1, ph[idx - 2], cz.b1, ph[idx - 1], cz.c1, ph[idx]);
-                        else d = cdiv(ph[idx + 1] - ph[idx - 1], cz.h2, cz.rh2);
-                        pz_buf[idx] = d;
-                    }
-                }
-            }
-        };
-
-        // d/dy and d/dz of a staged plane at an output column
-        auto dY = [&](const double* B, int idx, unsigned rf) -> double {
-            if (rf & 2u) return edge3(cy.a0, B[idx], cy.b0, B[idx + RK], cy.c0, B[idx + 2 * RK]);
-            if (rf & 4u) return edge3(cy.a1, B[idx - 2 * RK], cy.b1, B[idx - RK], cy.c1, B[idx]);
-            return cdiv(B[idx + RK] - B[idx - RK], cy.h2, cy.rh2);
-        };
-        auto dZ = [&](const double* B, int idx, unsigned cf) -> double {
-            if (cf & 2u) return edge3(cz.a0, B[idx], cz.b0, B[idx + 1], cz.c0, B[idx + 2]);
-            if (cf & 4u) return edge3(cz.a1, B[idx - 2], cz.b1, B[idx - 1], cz.c1, B[idx]);
-            return cdiv(B[idx + 1] - B[idx - 1], cz.h2, cz.rh2);
-        };
-
-        // ---- second derivatives, rho, sums at the own output columns of plane i ---------
-        auto output = [&](int i) {
+        // ---- phase 2: second derivatives, rho, sums at the output columns of plane i ---------
+        auto phase2 = [&](int i) {
             const double* const px_i = px_ring + (i % 3) * PLANE;
+            const double* const px_p = px_ring + ((i + 1) % 3) * PLANE;   // phi_x(i+1)   (== slot of i-2)
+            const double* const px_m = px_ring + ((i + 2) % 3) * PLANE;   // phi_x(i-1)
+            const int iedge = (i == 0) ? 1 : ((i == P.n0 - 1) ? 2 : 0);
             const double xxi = P.xx[i];
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                if (!(rowf[b] & 16u)) continue;
+#pragma unroll 1
+            for (int jr = 2 + ty; jr <= Tj + 1; jr += NW) {
+                const int base = jr * RK + tx;
+                const int jedge = (t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0);
+                const double yyj = yy_s[jr];
+                double rho2[2];
 #pragma unroll
                 for (int a = 0; a < 2; ++a) {
-                    if (!(colf[a] & 16u)) continue;
-                    const int idx = jr_[b] * RK + tx + 32 * a;
+                    const int idx = base + 32 * a;
+                    const unsigned cf = a ? cf1 : cf0;
                     double pxx;
-                    if (i == 0)
+                    if (iedge == 1)
                         pxx = edge3(cx.a0, px_ring[idx], cx.b0, px_ring[PLANE + idx], cx.c0, px_ring[2 * PLANE + idx]);
-                    else if (i == P.n0 - 1)
-                        pxx = edge3(cx.a1, px_ring[((i - 2) % 3) * PLANE + idx], cx.b1,
-                                    px_ring[((i - 1) % 3) * PLANE + idx], cx.c1, px_i[idx]);
+                    else if (iedge == 2)
+                        pxx = edge3(cx.a1, px_p[idx], cx.b1, px_m[idx], cx.c1, px_i[idx]);   // phi_x(n0-3), (n0-2), (n0-1)
                     else
-                        pxx = cdiv(px_ring[((i + 1) % 3) * PLANE + idx] - px_ring[((i + 2) % 3) * PLANE + idx],
-                                   cx.h2, cx.rh2);
-                    const double pxy = dY(px_i, idx, rowf[b]);
-                    const double pxz = dZ(px_i, idx, colf[a]);
-                    const double pyy = dY(py_buf, idx, rowf[b]);
-                    const double pyz = dZ(py_buf, idx, colf[a]);
-                    const double pzz = dZ(pz_buf, idx, colf[a]);
+                        pxx = cdiv(px_p[idx] - px_m[idx], cx.h2, cx.rh2);
+                    const double pxy = dY(px_i, idx, jedge);
+                    const double pxz = dZ(px_i, idx, cf);
+                    const double pyy = dY(py_buf, idx, jedge);
+                    const double pyz = dZ(py_buf, idx, cf);
+                    const double pzz = dZ(pz_buf, idx, cf);
                     // K_ij = -phi_ij: the sign cancels in K^2 and in K_ij K^ij (reproduce_rodal_exact.py:198-212)
                     const double tr = (pxx + pyy) + pzz;
                     const double diag = (pxx * pxx + pyy * pyy) + pzz * pzz;
                     const double off = (pxy * pxy + pxz * pxz) + pyz * pyz;
                     const double kk = fma(2.0, off, diag);     // 2.0*off is exact -> same rounding as diag + 2.0*off
-                    const double rho_adm = cdiv(tr * tr - kk, P.c16pi, P.rc16pi);
-                    const double e = rho_adm * P.dV;
-                    if (EMIT) {
-                        const long long j = j0 - 2 + jr_[b], k = k0 - 2 + tx + 32 * a;
-                        P.rho_out[((long long)(i - P.i_begin) * P.n1 + j) * P.n2 + k] = rho_adm;
-                    }
-                    const bool pos = e > 0.0, neg = e < 0.0;
-                    acc_pos += pos ? e : 0.0;
-                    acc_neg += neg ? e : 0.0;
-                    c_pos += pos; c_neg += neg; c_zero += (e == 0.0); c_nan += (e != e);
-                    if (NSH > 0) {
-                        bool in_[NSH > 0 ? NSH : 1];
-                        if (DT == IWB_F64) {
-                            const double s = (xxi + yyv[b]) + zzv[a];
-#pragma unroll
-                            for (int sh = 0; sh < NSH; ++sh) in_[sh] = s <= P.shell_thr[sh];
-                        } else {
-                            const float s = __fadd_rn(__fadd_rn((float)xxi, (float)yyv[b]), (float)zzv[a]);
-#pragma unroll
-                            for (int sh = 0; sh < NSH; ++sh) in_[sh] = s <= (float)P.shell_thr[sh];
-                        }
-#pragma unroll
-                        for (int sh = 0; sh < NSH; ++sh) {
-                            sh_pos[sh] += (in_[sh] && pos) ? e : 0.0;
-                            sh_neg[sh] += (in_[sh] && neg) ? e : 0.0;
-                            sh_cnt[sh] += in_[sh];
-                        }
-                    }
+                    rho2[a] = cdiv(tr * tr - kk, P.c16pi, P.rc16pi);
                 }
+                if (EMIT) {
+                    const long long j = j0 - 2 + jr, k = k0 - 2 + tx;
+                    double* dst = P.rho_out + ((long long)(i - P.i_begin) * P.n1 + j) * P.n2 + k;
+                    if (cf0 & 16u) dst[0] = rho2[0];
+                    if (cf1 & 16u) dst[32] = rho2[1];
+                }
+                tally(rho2[0] * P.dV, (cf0 & 16u) != 0, yyj, zz0, xxi);
+                tally(rho2[1] * P.dV, (cf1 & 16u) != 0, yyj, zz1, xxi);
             }
         };
 
@@ -305,7 +316,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                     else vals[q] += o;
                 }
             }
-            double* scratch = pz_buf;           // free after the trailing barrier of output()
+            double* scratch = pz_buf;           // free after the trailing barrier of phase 2
             if (tx == 0) {
 #pragma unroll
                 for (int q = 0; q < NV; ++q) scratch[ty * NV + q] = vals[q];
@@ -335,29 +346,36 @@ k_energy3d(const __grid_constant__ K3Params P)
             __syncthreads();
             acc_pos = 0.0; acc_neg = 0.0; c_pos = c_neg = c_zero = c_nan = 0;
 #pragma unroll
-            for (int s = 0; s < NSH; ++s) { sh_pos[s] = 0.0; sh_neg[s] = 0.0; sh_cnt[s] = 0; }
+            for (int s = 0; s < NSHA; ++s) { sh_pos[s] = 0.0; sh_neg[s] = 0.0; sh_cnt[s] = 0; }
         };
 
         // ---- march ------------------------------------------------------------------------
-        __syncthreads();                 // previous item's shared memory is dead
+        __syncthreads();                 // yy_s visible
         int produced = pstart - 1;
         bool px_last_done = false;
         for (int i = i0; i < i1; ++i) {
             const int target = min(max(i + 2, 3), P.n0 - 1);
             const int early = min(target, i + 2);
-            while (produced < early) produce(++produced);
-            if (i == i0) __syncthreads();            // prologue planes visible to neighbours
-            inplane(i);
+            if (i == i0) {
+                while (produced < early) phase1(++produced, -1);
+                __syncthreads();                     // prologue planes visible to neighbours
+                phase1(-1, i);
+            } else if (produced < early) {
+                ++produced;
+                phase1(produced, i);                 // steady state: phi(i+2) together with phi_y/phi_z(i)
+            } else {
+                phase1(-1, i);
+            }
             if (produced < target) {                 // only i == 0: phi(3) reuses the slot of phi(0)
                 __syncthreads();
-                produce(++produced);
+                phase1(++produced, -1);
             }
             if (!px_last_done && max(i - 1, 0) >= P.n0 - 3 && produced == P.n0 - 1) {
                 produce_px_last();
                 px_last_done = true;
             }
             __syncthreads();
-            output(i);
+            phase2(i);
             __syncthreads();
             if (((i + 1) % FLUSH) == 0 || i == i1 - 1) flush(i / FLUSH);
         }
