@@ -233,6 +233,7 @@ int iwb_energy3d(iwb_handle* h, const iwb_params3d* p, iwb_result* out)
     IWB_CUDA(cudaStreamSynchronize(c.stream));
     memset(out, 0, sizeof(*out));
     unpack_row((const double*)c.h_out.p, p->nshell, out);
+    out->cnt_nan = (int64_t)(p->i_end - p->i_begin) * p->n1 * p->n2 - out->cnt_pos - out->cnt_neg - out->cnt_zero;
     float ms = 0;
     IWB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
     out->kernel_ms = ms;
@@ -293,6 +294,8 @@ int iwb_energy3d_batch(iwb_handle* h, int npoints, const iwb_params3d* pts, iwb_
             IWB_CUDA(cudaStreamSynchronize(c.stream));
             memset(&outs[base + q], 0, sizeof(iwb_result));
             unpack_row((const double*)c.h_out.p, pts[base + q].nshell, &outs[base + q]);
+            outs[base + q].cnt_nan = (int64_t)(pts[base + q].i_end - pts[base + q].i_begin) * pts[base + q].n1 * pts[base + q].n2 -
+                                     outs[base + q].cnt_pos - outs[base + q].cnt_neg - outs[base + q].cnt_zero;
             float ms = 0;
             IWB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
             outs[base + q].kernel_ms = ms;

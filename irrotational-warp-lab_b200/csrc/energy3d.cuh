@@ -24,6 +24,8 @@
 // the tiles in fixed order.  Flush blocks are aligned to the GLOBAL plane index, so the
 // result is bit-identical for any slab decomposition along i.
 #pragma once
+#include <type_traits>
+
 #include "iwb_device.cuh"
 #include "../../include/iwb200.h"
 
@@ -116,7 +118,7 @@ k_energy3d(const __grid_constant__ K3Params P)
         // ---- accumulators (registers) -------------------------------------------------
         double acc_pos = 0.0, acc_neg = 0.0;
         double sh_pos[NSHA], sh_neg[NSHA];
-        int c_pos = 0, c_neg = 0, c_zero = 0, c_nan = 0;
+        int c_pos = 0, c_neg = 0, c_zero = 0;
         int sh_cnt[NSHA];
 #pragma unroll
         for (int s = 0; s < NSHA; ++s) { sh_pos[s] = 0.0; sh_neg[s] = 0.0; sh_cnt[s] = 0; }
@@ -124,26 +126,31 @@ k_energy3d(const __grid_constant__ K3Params P)
         const int w0 = min(max(i0 - 1, 0), P.n0 - 3);
         const int pstart = max(0, w0 - 1);
 
-        // d/dz (along lanes) of a staged plane; one-sided at the global faces
-        auto dZ = [&](const double* B, int idx, unsigned cf) -> double {
+        // d/dz (along lanes) and d/dy (along rows) of a staged plane.  The EDGE = false flavours are
+        // the pure interior formula (no branches: the two columns of a thread interleave freely);
+        // EDGE = true adds the one-sided formulas at the global faces.
+        auto dZ = [&](const double* B, int idx, unsigned cf, auto edge_tag) -> double {
             double d = cdiv(B[idx + 1] - B[idx - 1], cz.h2, cz.rh2);
-            if (t_kedge) {
+            if (decltype(edge_tag)::value) {
                 if (cf & 2u) d = edge3(cz.a0, B[idx], cz.b0, B[idx + 1], cz.c0, B[idx + 2]);
                 else if (cf & 4u) d = edge3(cz.a1, B[idx - 2], cz.b1, B[idx - 1], cz.c1, B[idx]);
             }
             return d;
         };
-        // d/dy (along rows); jedge: 0 interior, 1 row j == 0, 2 row j == n1-1 (warp-uniform)
-        auto dY = [&](const double* B, int idx, int jedge) -> double {
-            if (jedge == 1) return edge3(cy.a0, B[idx], cy.b0, B[idx + RK], cy.c0, B[idx + 2 * RK]);
-            if (jedge == 2) return edge3(cy.a1, B[idx - 2 * RK], cy.b1, B[idx - RK], cy.c1, B[idx]);
+        // jedge: 0 interior, 1 row j == 0, 2 row j == n1-1 (warp-uniform)
+        auto dY = [&](const double* B, int idx, int jedge, auto edge_tag) -> double {
+            if (decltype(edge_tag)::value) {
+                if (jedge == 1) return edge3(cy.a0, B[idx], cy.b0, B[idx + RK], cy.c0, B[idx + 2 * RK]);
+                if (jedge == 2) return edge3(cy.a1, B[idx - 2 * RK], cy.b1, B[idx - RK], cy.c1, B[idx]);
+            }
             return cdiv(B[idx + RK] - B[idx - RK], cy.h2, cy.rh2);
         };
 
         // ---- phase 1 -----------------------------------------------------------------------
         // p >= 0: produce phi(p) and the x-derivative it completes (own columns only).
         // ip >= 0: phi_y(ip), phi_z(ip) from the phi(ip) plane (reads neighbours' columns).
-        auto phase1 = [&](int p, int ip) {
+        auto phase1 = [&](int p, int ip, auto edge_tag) {
+            constexpr bool EDGE = decltype(edge_tag)::value;
             double xp = 0.0, xxp = 0.0;
             double* ph_p = phi_ring;
             const double *ph_m1 = phi_ring, *ph_m2 = phi_ring;
@@ -156,7 +163,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                 ph_m2 = phi_ring + ((p + 1) % 3) * PLANE;      // plane p-2
                 px_w = px_ring + ((p + 2) % 3) * PLANE;        // phi_x(p-1)
                 do_px = (p - 2 >= pstart);                     // interior formula
-                do_px0 = (p == 2) && (pstart == 0);            // phi_x(0), one-sided
+                do_px0 = EDGE && (p == 2) && (pstart == 0);    // phi_x(0), one-sided
             }
             const double* const ph_i = phi_ring + ((ip >= 0 ? ip : 0) % 3) * PLANE;
 #pragma unroll 1
@@ -180,20 +187,20 @@ k_energy3d(const __grid_constant__ K3Params P)
                         px_w[base] = cdiv(f[0] - ph_m2[base], cx.h2, cx.rh2);
                         px_w[base + 32] = cdiv(f[1] - ph_m2[base + 32], cx.h2, cx.rh2);
                     }
-                    if (do_px0) {
+                    if (EDGE && do_px0) {
                         px_ring[base] = edge3(cx.a0, ph_m2[base], cx.b0, ph_m1[base], cx.c0, f[0]);
                         px_ring[base + 32] = edge3(cx.a0, ph_m2[base + 32], cx.b0, ph_m1[base + 32], cx.c0, f[1]);
                     }
                 }
                 if (ip >= 0) {
                     if (jr >= py_lo && jr <= py_hi) {
-                        const int jedge = (t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0);
-                        py_buf[base] = dY(ph_i, base, jedge);
-                        py_buf[base + 32] = dY(ph_i, base + 32, jedge);
+                        const int jedge = EDGE ? ((t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0)) : 0;
+                        py_buf[base] = dY(ph_i, base, jedge, edge_tag);
+                        py_buf[base + 32] = dY(ph_i, base + 32, jedge, edge_tag);
                     }
                     if (jr >= 2 && jr <= Tj + 1) {
-                        pz_buf[base] = dZ(ph_i, base, cf0);
-                        pz_buf[base + 32] = dZ(ph_i, base + 32, cf1);
+                        pz_buf[base] = dZ(ph_i, base, cf0, edge_tag);
+                        pz_buf[base + 32] = dZ(ph_i, base + 32, cf1, edge_tag);
                     }
                 }
             }
@@ -216,44 +223,73 @@ k_energy3d(const __grid_constant__ K3Params P)
             }
         };
 
-        // ---- predicated sums of one point (reproduce_rodal_exact.py:57-61, 220-224) ----------
-        auto tally = [&](double e, bool out_col, double yyj, double zzk, double xxi) {
-            const bool pos = out_col && (e > 0.0), neg = out_col && (e < 0.0);
-            acc_pos += pos ? e : 0.0;
-            acc_neg += neg ? e : 0.0;
-            c_pos += pos; c_neg += neg;
-            c_zero += (out_col && e == 0.0); c_nan += (out_col && e != e);
+        // ---- predicated sums of one row's two points (reproduce_rodal_exact.py:57-61, 220-224) ------
+        // NaN points are not counted here: every point is exactly one of pos / neg / zero / NaN, so the
+        // host derives cnt_nan from the number of points.  The shell sums are skipped for a warp none of
+        // whose lanes lies inside any shell (adding +0.0 is the identity, so this does not
+        // change a single bit of the result).
+        auto tally2 = [&](const double (&e)[2], double yyj, double xxi) {
+            const bool out0 = (cf0 & 16u) != 0, out1 = (cf1 & 16u) != 0;
+            const bool p0 = out0 && (e[0] > 0.0), n0 = out0 && (e[0] < 0.0);
+            const bool p1 = out1 && (e[1] > 0.0), n1 = out1 && (e[1] < 0.0);
+            const double ep0 = p0 ? e[0] : 0.0, en0 = n0 ? e[0] : 0.0;
+            const double ep1 = p1 ? e[1] : 0.0, en1 = n1 ? e[1] : 0.0;
+            acc_pos += ep0; acc_neg += en0;
+            acc_pos += ep1; acc_neg += en1;
+            if (p0) ++c_pos;
+            if (p1) ++c_pos;
+            if (n0) ++c_neg;
+            if (n1) ++c_neg;
+            if (out0 && (((__double2hiint(e[0]) & 0x7fffffff) | __double2loint(e[0])) == 0)) ++c_zero;
+            if (out1 && (((__double2hiint(e[1]) & 0x7fffffff) | __double2loint(e[1])) == 0)) ++c_zero;
             if (NSH > 0) {
-                bool in_[NSHA];
+                bool in0[NSHA], in1[NSHA];
+                bool any_in = false;
                 if (DT == IWB_F64) {
-                    const double s = (xxi + yyj) + zzk;
+                    const double sxy = xxi + yyj;
+                    const double s0 = sxy + zz0, s1 = sxy + zz1;
 #pragma unroll
-                    for (int sh = 0; sh < NSH; ++sh) in_[sh] = out_col && (s <= P.shell_thr[sh]);
+                    for (int sh = 0; sh < NSH; ++sh) {
+                        in0[sh] = out0 && (s0 <= P.shell_thr[sh]);
+                        in1[sh] = out1 && (s1 <= P.shell_thr[sh]);
+                        any_in |= in0[sh] | in1[sh];
+                    }
                 } else {
-                    const float s = __fadd_rn(__fadd_rn((float)xxi, (float)yyj), (float)zzk);
+                    const float sxy = __fadd_rn((float)xxi, (float)yyj);
+                    const float s0 = __fadd_rn(sxy, (float)zz0), s1 = __fadd_rn(sxy, (float)zz1);
 #pragma unroll
-                    for (int sh = 0; sh < NSH; ++sh) in_[sh] = out_col && (s <= (float)P.shell_thr[sh]);
+                    for (int sh = 0; sh < NSH; ++sh) {
+                        in0[sh] = out0 && (s0 <= (float)P.shell_thr[sh]);
+                        in1[sh] = out1 && (s1 <= (float)P.shell_thr[sh]);
+                        any_in |= in0[sh] | in1[sh];
+                    }
                 }
+                if (__any_sync(0xffffffffu, any_in)) {
 #pragma unroll
-                for (int sh = 0; sh < NSH; ++sh) {
-                    sh_pos[sh] += (in_[sh] && pos) ? e : 0.0;
-                    sh_neg[sh] += (in_[sh] && neg) ? e : 0.0;
-                    sh_cnt[sh] += in_[sh];
+                    for (int sh = 0; sh < NSH; ++sh) {
+                        sh_pos[sh] += in0[sh] ? ep0 : 0.0;
+                        sh_neg[sh] += in0[sh] ? en0 : 0.0;
+                        sh_pos[sh] += in1[sh] ? ep1 : 0.0;
+                        sh_neg[sh] += in1[sh] ? en1 : 0.0;
+                        if (in0[sh]) ++sh_cnt[sh];
+                        if (in1[sh]) ++sh_cnt[sh];
+                    }
                 }
             }
         };
 
         // ---- phase 2: second derivatives, rho, sums at the output columns of plane i ---------
-        auto phase2 = [&](int i) {
+        auto phase2 = [&](int i, auto edge_tag) {
+            constexpr bool EDGE = decltype(edge_tag)::value;
             const double* const px_i = px_ring + (i % 3) * PLANE;
             const double* const px_p = px_ring + ((i + 1) % 3) * PLANE;   // phi_x(i+1)   (== slot of i-2)
             const double* const px_m = px_ring + ((i + 2) % 3) * PLANE;   // phi_x(i-1)
-            const int iedge = (i == 0) ? 1 : ((i == P.n0 - 1) ? 2 : 0);
+            const int iedge = EDGE ? ((i == 0) ? 1 : ((i == P.n0 - 1) ? 2 : 0)) : 0;
             const double xxi = P.xx[i];
 #pragma unroll 1
             for (int jr = 2 + ty; jr <= Tj + 1; jr += NW) {
                 const int base = jr * RK + tx;
-                const int jedge = (t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0);
+                const int jedge = EDGE ? ((t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0)) : 0;
                 const double yyj = yy_s[jr];
                 double rho2[2];
 #pragma unroll
@@ -261,17 +297,17 @@ k_energy3d(const __grid_constant__ K3Params P)
                     const int idx = base + 32 * a;
                     const unsigned cf = a ? cf1 : cf0;
                     double pxx;
-                    if (iedge == 1)
+                    if (EDGE && iedge == 1)
                         pxx = edge3(cx.a0, px_ring[idx], cx.b0, px_ring[PLANE + idx], cx.c0, px_ring[2 * PLANE + idx]);
-                    else if (iedge == 2)
+                    else if (EDGE && iedge == 2)
                         pxx = edge3(cx.a1, px_p[idx], cx.b1, px_m[idx], cx.c1, px_i[idx]);   // phi_x(n0-3), (n0-2), (n0-1)
                     else
                         pxx = cdiv(px_p[idx] - px_m[idx], cx.h2, cx.rh2);
-                    const double pxy = dY(px_i, idx, jedge);
-                    const double pxz = dZ(px_i, idx, cf);
-                    const double pyy = dY(py_buf, idx, jedge);
-                    const double pyz = dZ(py_buf, idx, cf);
-                    const double pzz = dZ(pz_buf, idx, cf);
+                    const double pxy = dY(px_i, idx, jedge, edge_tag);
+                    const double pxz = dZ(px_i, idx, cf, edge_tag);
+                    const double pyy = dY(py_buf, idx, jedge, edge_tag);
+                    const double pyz = dZ(py_buf, idx, cf, edge_tag);
+                    const double pzz = dZ(pz_buf, idx, cf, edge_tag);
                     // K_ij = -phi_ij: the sign cancels in K^2 and in K_ij K^ij (reproduce_rodal_exact.py:198-212)
                     const double tr = (pxx + pyy) + pzz;
                     const double diag = (pxx * pxx + pyy * pyy) + pzz * pzz;
@@ -285,8 +321,8 @@ k_energy3d(const __grid_constant__ K3Params P)
                     if (cf0 & 16u) dst[0] = rho2[0];
                     if (cf1 & 16u) dst[32] = rho2[1];
                 }
-                tally(rho2[0] * P.dV, (cf0 & 16u) != 0, yyj, zz0, xxi);
-                tally(rho2[1] * P.dV, (cf1 & 16u) != 0, yyj, zz1, xxi);
+                const double e2[2] = {rho2[0] * P.dV, rho2[1] * P.dV};
+                tally2(e2, yyj, xxi);
             }
         };
 
@@ -298,7 +334,7 @@ k_energy3d(const __grid_constant__ K3Params P)
             vals[2] = __longlong_as_double((long long)c_pos);
             vals[3] = __longlong_as_double((long long)c_neg);
             vals[4] = __longlong_as_double((long long)c_zero);
-            vals[5] = __longlong_as_double((long long)c_nan);
+            vals[5] = __longlong_as_double(0LL);      // cnt_nan is derived on the host
 #pragma unroll
             for (int s = 0; s < NSH; ++s) {
                 vals[6 + s] = sh_pos[s];
@@ -344,38 +380,44 @@ k_energy3d(const __grid_constant__ K3Params P)
                 P.partial[((size_t)fb * ntiles + tile) * ROW + slot] = acc;
             }
             __syncthreads();
-            acc_pos = 0.0; acc_neg = 0.0; c_pos = c_neg = c_zero = c_nan = 0;
+            acc_pos = 0.0; acc_neg = 0.0; c_pos = c_neg = c_zero = 0;
 #pragma unroll
             for (int s = 0; s < NSHA; ++s) { sh_pos[s] = 0.0; sh_neg[s] = 0.0; sh_cnt[s] = 0; }
         };
 
         // ---- march ------------------------------------------------------------------------
         __syncthreads();                 // yy_s visible
+        const bool tile_edge = t_jlo || t_jhi || t_kedge;
+        auto run_phase1 = [&](int p, int ip) {
+            if (tile_edge || (p == 2 && pstart == 0)) phase1(p, ip, std::true_type{});
+            else phase1(p, ip, std::false_type{});
+        };
         int produced = pstart - 1;
         bool px_last_done = false;
         for (int i = i0; i < i1; ++i) {
             const int target = min(max(i + 2, 3), P.n0 - 1);
             const int early = min(target, i + 2);
             if (i == i0) {
-                while (produced < early) phase1(++produced, -1);
+                while (produced < early) run_phase1(++produced, -1);
                 __syncthreads();                     // prologue planes visible to neighbours
-                phase1(-1, i);
+                run_phase1(-1, i);
             } else if (produced < early) {
                 ++produced;
-                phase1(produced, i);                 // steady state: phi(i+2) together with phi_y/phi_z(i)
+                run_phase1(produced, i);             // steady state: phi(i+2) together with phi_y/phi_z(i)
             } else {
-                phase1(-1, i);
+                run_phase1(-1, i);
             }
             if (produced < target) {                 // only i == 0: phi(3) reuses the slot of phi(0)
                 __syncthreads();
-                phase1(++produced, -1);
+                run_phase1(++produced, -1);
             }
             if (!px_last_done && max(i - 1, 0) >= P.n0 - 3 && produced == P.n0 - 1) {
                 produce_px_last();
                 px_last_done = true;
             }
             __syncthreads();
-            phase2(i);
+            if (tile_edge || i == 0 || i == P.n0 - 1) phase2(i, std::true_type{});
+            else phase2(i, std::false_type{});
             __syncthreads();
             if (((i + 1) % FLUSH) == 0 || i == i1 - 1) flush(i / FLUSH);
         }
