@@ -1,0 +1,322 @@
+#!/usr/bin/env python3
+"""Headline benchmark: 3D energy-condition evaluation, fp64, n = 1024^3 (BASELINE.json config 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 1024] [--impl ours|reference]
+
+One *step* = one full evaluation of the hot path on the synthetic (analytic) grid rho=5 sigma=4
+v=1 extent=66, shells r<=40 / r<=60: fused kernel -> fixed-order tile reduction -> (N>1: NCCL
+all-gather of the 15 KB partial table) -> fixed-order row reduction -> 240-byte result to the host.
+
+N = 1 runs in this process; N > 1 is launched by torchrun, one rank per GPU, each rank owning one
+slab of axis 0 (weak scaling is NOT used: the volume is fixed, so "scaling": "strong").
+
+Printed JSON (one line, rank 0):
+  value   : Gpoints/s, whole job, inputs (coordinates) resident in HBM -- CUDA events on the
+            launching stream, summed over K steps, max over ranks
+  e2e     : same metric through the public API (backend.compute_energy_3d / distributed.
+            compute_energy_3d_sharded) with host numpy coordinates copied from pinned memory and the
+            result read back every step, wall clock
+  roofline: FP64-pipe bound (no dense contraction, ~0 HBM bytes/point); see DESIGN.md §6
+  cpu_baseline: the NumPy restatement of the reference (oracle/oracle_np.py, 1 core) on a bounded sample
+`--impl reference` times that CPU path alone (the reference is pure NumPy, single-threaded).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+RHO, SIGMA, V, EXTENT = 5.0, 4.0, 1.0, 66.0
+SHELLS = [40.0, 60.0]
+METRIC = "3D Gpoints/s (fp64, n=1024^3)"
+# FP64 issue slots per grid point.  CONTRACT = SURVEY.md §8(d) / BASELINE.md §4 (IEEE divisions at 9 slots
+# each, exp/log1p on every point).  EXACT_ALG = the bit-exact algorithm this engine runs, counted from
+# SASS with ncu: constant-divisor divisions in 3 slots, exp/log1p only inside the wall.
+SLOTS_CONTRACT = 271.0
+SLOTS_EXACT_ALG = 114.0
+CPU_SAMPLE_N = 256
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        sm, smax, reasons = [], [], set()
+        for t, line in self.rows:
+            if t < t0 or t > t1:
+                continue
+            f = [c.strip() for c in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(n=CPU_SAMPLE_N, reps=2):
+    """NumPy restatement of the reference path (oracle/oracle_np.py), one core, bounded sample."""
+    from oracle import oracle_np
+    best = float("inf")
+    for rep in range(reps + 1):
+        t0 = time.perf_counter()
+        oracle_np.energy_3d(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, n=n, shells=SHELLS)
+        dt = time.perf_counter() - t0
+        if rep > 0:
+            best = min(best, dt)
+    return {"value": n ** 3 / best / 1e9, "unit": "Gpoints/s", "cores": 1, "kind": "port",
+            "sample": f"n={n}^3 volume, same rho/sigma/v/extent/shells, NumPy restatement of compute_energy_3d "
+                      f"(single-threaded like the reference), best of {reps} after 1 warm-up",
+            "host_cores_available": os.cpu_count()}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm on the host (NumPy port, single-threaded)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle_np
+    n = CPU_SAMPLE_N
+    for _ in range(min(args.warmup, 1)):
+        oracle_np.energy_3d(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, n=n, shells=SHELLS)
+    steps = min(args.steps, 5)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_np.energy_3d(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, n=n, shells=SHELLS)
+    dt = (time.perf_counter() - t0) / steps
+    val = n ** 3 / dt / 1e9
+    sample = (f"each step = one n={n}^3 evaluation (bounded sample of the n={args.n}^3 workload: the reference needs "
+              f"~224 B/point, i.e. ~240 GB at 1024^3); NumPy port oracle/oracle_np.py, 1 thread")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Gpoints/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3D n={args.n}^3 fp64 energy-condition evaluation, rho=5 sigma=4 v=1 extent=66, shells 40/60"},
+        "cpu_baseline": {"value": val, "unit": "Gpoints/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=1024)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args(argv)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from irrotational_warp_lab_b200 import backend, distributed, sharding
+    from irrotational_warp_lab_b200._capi import ROW_WIDTH
+    from irrotational_warp_lab_b200.engine import get_engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the b200 engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    warmup = max(args.warmup, 3)
+    steps = max(args.steps, 1)
+    n = args.n
+    eng = get_engine(local_rank)
+    x = np.linspace(-EXTENT, EXTENT, n)
+    dx = float(x[1] - x[0])
+    i_begin, i_end = sharding.slab_bounds(n, world)[rank]
+    nfb = sharding.num_flush_blocks(n)
+    r0, r1 = sharding.rows_of_slab(i_begin, i_end)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- value: coordinates resident on the device, CUDA events ----------------------------
+    plan = eng.plan3d(x=x, y=x, z=x, dx=dx, dy=dx, dz=dx, rho=RHO, sigma=SIGMA, v=V, dtype="float64", shells=SHELLS,
+                      i_begin=i_begin, i_end=i_end) if i_end > i_begin else None
+    table = torch.zeros((nfb, ROW_WIDTH), dtype=torch.float64, device=dev)
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+
+    def resident_step():
+        if plan is not None:
+            plan.run_async(table.data_ptr(), stream.cuda_stream)
+        full = sharding.all_gather_table(table[r0:r1], n, world) if world > 1 else table
+        return eng.reduce_table(full.data_ptr(), nfb, len(SHELLS), stream.cuda_stream)
+
+    for _ in range(warmup):
+        res = resident_step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t_region0 = time.perf_counter()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s in range(steps):
+        flush_buf.zero_()                       # L2 flush between timed iterations (outside the event pair)
+        ev[s][0].record(stream)
+        res = resident_step()
+        ev[s][1].record(stream)
+    barrier()
+    t_region1 = time.perf_counter()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    ms_per_step = dev_ms / steps
+    value = n ** 3 / (ms_per_step * 1e-3) / 1e9
+    launches_value = steps * ((2 if plan is not None else 0) + 1)      # k_energy3d, k_reduce_tiles, k_reduce_rows
+
+    # kernel-only duration of the dominant kernel (rank 0's slab), CUDA events on its launching stream
+    kern_ms = []
+    if plan is not None:
+        for _ in range(min(steps, 5)):
+            flush_buf.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            plan.run_async(table.data_ptr(), stream.cuda_stream)
+            b.record(stream)
+            torch.cuda.synchronize(dev)
+            kern_ms.append(a.elapsed_time(b))
+    kern_ms_avg = sum(kern_ms) / max(len(kern_ms), 1)
+
+    # ---------------- e2e: public API, host buffers, wall clock ------------------------------------------
+    def api_step():
+        if world > 1:
+            return distributed.compute_energy_3d_sharded(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, n=n, shells=SHELLS)
+        return backend.compute_energy_3d(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, n=n, shells=SHELLS)
+
+    for _ in range(warmup):
+        run = api_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run = api_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = n ** 3 * steps / e2e_s / 1e9
+    launches_e2e = steps * 3
+    if rank == 0:
+        sampler.stop()
+    clocks = sampler.summary(t_region0, time.perf_counter()) if rank == 0 else None
+
+    # sanity: the two paths agree bit-for-bit and look like the reference's convergence series
+    assert run["energies"]["e_pos"] == res["e_pos"] and run["energies"]["e_neg"] == res["e_neg"], "paths disagree"
+    if n == 1024:
+        assert 1.058 < res["e_pos"] < 1.08 and -1.03 < res["e_neg"] < -1.005, res
+
+    if rank == 0:
+        peak = eng.measure_fma_peak(False)
+        pts_per_s_kernel = (i_end - i_begin) * n * n / (kern_ms_avg * 1e-3) if kern_ms_avg else 0.0
+        achieved_contract = pts_per_s_kernel * SLOTS_CONTRACT * 2 / 1e12
+        achieved_exact = pts_per_s_kernel * SLOTS_EXACT_ALG * 2 / 1e12
+        peaks_file = {}
+        try:
+            peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
+        alg_bytes = 8.0 * (2 * n + n + n) + 8.0 * ROW_WIDTH * (r1 - r0)          # coordinates in, table rows out
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3D n={n}^3 fp64 energy-condition evaluation (BASELINE config 4): rho=5 sigma=4 v=1 "
+                                   f"extent=66, shells r<=40 and r<=60, exact (IEEE-replay) mode",
+                       "sharding": f"{world} slab(s) of axis 0, analytic halo recompute, all-gather of a "
+                                   f"{nfb}x{ROW_WIDTH} f64 table" if world > 1 else "single GPU",
+                       "l2": "256 MiB buffer written between timed steps (inputs are 32 KB of coordinates)",
+                       "timing": "per-step CUDA-event pairs on the launching stream, summed; max over ranks"},
+            "e2e": {"value": e2e_value, "unit": "Gpoints/s", "h2d_bytes_per_step": 8 * 4 * n,
+                    "d2h_bytes_per_step": 8 * ROW_WIDTH, "ms_per_step": e2e_s / steps * 1e3,
+                    "api": "distributed.compute_energy_3d_sharded" if world > 1 else "backend.compute_energy_3d"},
+            "gpu_launches": launches_value + launches_e2e,
+            "roofline": {
+                "bound": "fp64", "kernel": "k_energy3d", "unit": "TFLOP/s",
+                "achieved": achieved_exact, "peak": peak["tflops"], "frac": achieved_exact / peak["tflops"],
+                "traffic": None,
+                "slots_per_point": SLOTS_EXACT_ALG,
+                "note": "FP64-pipe bound: achieved = kernel points/s x 114 FP64 issue slots/point x 2 (slots of the "
+                        "bit-exact algorithm, counted from SASS, DESIGN.md §6); peak = register-resident DFMA "
+                        "microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 vector figure)",
+                "kernel_ms": kern_ms_avg, "kernel_points": (i_end - i_begin) * n * n,
+                "contract": {"slots_per_point": SLOTS_CONTRACT, "achieved": achieved_contract,
+                             "frac": achieved_contract / peak["tflops"],
+                             "note": "SURVEY.md §8(d) figure (9-slot IEEE divisions, exp/log1p at every point)"},
+                "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kern_ms_avg * 1e-3) / 1e9
+                        if kern_ms_avg else None, "peak_gbs": hbm_peak, "note": "never binding: ~0 B/point"},
+                "peak_sm_mhz_effective": peak["sm_mhz_effective"],
+            },
+            "clocks": clocks,
+            "result": {"e_pos": res["e_pos"], "e_neg": res["e_neg"], "cnt_neg": res["cnt_neg"], "cnt_pos": res["cnt_pos"]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if plan is not None:
+        plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

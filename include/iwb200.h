@@ -122,6 +122,15 @@ int iwb_energy3d(iwb_handle *h, const iwb_params3d *p, iwb_result *out);
  * stream) WITHOUT synchronising.  i_begin must be a multiple of IWB_FLUSH_PLANES. */
 int iwb_energy3d_slab_async(iwb_handle *h, const iwb_params3d *p, double *table_device, void *stream);
 
+/* Prepared evaluation: coordinates uploaded and constants derived once, then launched any number
+ * of times with NO host<->device traffic (kernel + tile reduction into `table_device` only).
+ * This is what a resident-input measurement and a repeated-evaluation driver use.  rho_out, if
+ * set, must be a device pointer. */
+typedef struct iwb_plan3d iwb_plan3d;
+int iwb_plan3d_create(iwb_handle *h, const iwb_params3d *p, iwb_plan3d **out);
+int iwb_plan3d_run_async(iwb_plan3d *plan, double *table_device, void *stream);
+int iwb_plan3d_destroy(iwb_plan3d *plan);
+
 /* Fixed-order sum of a complete table (device pointer) into *out; blocking. */
 int iwb_reduce_table(iwb_handle *h, const double *table_device, int nrows, int nshell, void *stream,
                      iwb_result *out);

@@ -91,6 +91,9 @@ SYMBOLS = {
                                   C.c_char_p, C.c_int]),
     "iwb_energy3d": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.POINTER(Result)]),
     "iwb_energy3d_slab_async": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.c_void_p, C.c_void_p]),
+    "iwb_plan3d_create": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.POINTER(C.c_void_p)]),
+    "iwb_plan3d_run_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "iwb_plan3d_destroy": (C.c_int, [C.c_void_p]),
     "iwb_reduce_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(Result)]),
     "iwb_energy3d_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Params3D), C.POINTER(Result)]),
     "iwb_energy_axisym": (C.c_int, [C.c_void_p, C.POINTER(ParamsAxisym), C.POINTER(Result)]),

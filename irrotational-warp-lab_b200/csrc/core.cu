@@ -147,7 +147,7 @@ int iwb_create(int device_id, iwb_handle** out)
         IWB_CUDA(cudaEventCreate(&h->scr[s].ev1));
     }
     const char* cfg = getenv("IWB_K3_CONFIG");
-    h->k3_config = cfg ? atoi(cfg) : 0;
+    h->k3_config = cfg ? atoi(cfg) : 1;
     const char* sl = getenv("IWB_K3_SEG_LEN");
     h->k3_seg_len = sl ? atoi(sl) : 0;
     *out = h;

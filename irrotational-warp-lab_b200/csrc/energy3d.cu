@@ -97,10 +97,16 @@ static int validate(const iwb_params3d* p)
     return IWB_OK;
 }
 
-// Uploads coordinates, fills K3Params and launches the fused kernel + the tile reduction on c.stream.
-// `table` is the [ceil(n0/FLUSH)][ROW] device table; only the rows of [i_begin, i_end) are written.
-static int enqueue_slab(iwb_handle* h, Scratch& c, const iwb_params3d* p, double* table, cudaStream_t st,
-                        double* rho_dev)
+// Everything a launch needs besides the output table.
+struct Launch3 {
+    K3Params P;
+    int dtype, nshell, cfg_id, ntiles, fb0, fb1;
+    bool emit;
+};
+
+// Stages coordinates into `hc` (pinned) -> `dc` (device) on `st` and fills the launch record.
+static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, DevBuf& coords, DevBuf& partial,
+                        cudaStream_t st, double* rho_dev, Launch3* L)
 {
     const int n0 = p->n0, n1 = p->n1, n2 = p->n2;
     const int cfg_id = config_is_built(h->k3_config, p->dtype, p->nshell, rho_dev != nullptr) ? h->k3_config : 0;
@@ -108,9 +114,9 @@ static int enqueue_slab(iwb_handle* h, Scratch& c, const iwb_params3d* p, double
 
     // coordinates: x, x*x, y*y, z*z (squares rounded once in the coordinate dtype, as x*x is in NumPy)
     const size_t ncoord = (size_t)2 * n0 + n1 + n2;
-    IWB_CUDA(c.h_coords.reserve(ncoord * sizeof(double)));
-    IWB_CUDA(c.coords.reserve(ncoord * sizeof(double)));
-    double* hc = (double*)c.h_coords.p;
+    IWB_CUDA(h_coords.reserve(ncoord * sizeof(double)));
+    IWB_CUDA(coords.reserve(ncoord * sizeof(double)));
+    double* hc = (double*)h_coords.p;
     double *hx = hc, *hxx = hc + n0, *hyy = hc + 2 * n0, *hzz = hc + 2 * n0 + n1;
     if (p->dtype == IWB_F64) {
         for (int i = 0; i < n0; ++i) { hx[i] = p->x[i]; hxx[i] = p->x[i] * p->x[i]; }
@@ -121,10 +127,9 @@ static int enqueue_slab(iwb_handle* h, Scratch& c, const iwb_params3d* p, double
         for (int j = 0; j < n1; ++j) { float f = (float)p->y[j]; hyy[j] = (double)(f * f); }
         for (int k = 0; k < n2; ++k) { float f = (float)p->z[k]; hzz[k] = (double)(f * f); }
     }
-    // the pinned staging buffer may still feed an earlier async copy on this stream
-    IWB_CUDA(cudaMemcpyAsync(c.coords.p, hc, ncoord * sizeof(double), cudaMemcpyHostToDevice, st));
+    IWB_CUDA(cudaMemcpyAsync(coords.p, hc, ncoord * sizeof(double), cudaMemcpyHostToDevice, st));
 
-    K3Params P;
+    K3Params& P = L->P;
     memset(&P, 0, sizeof(P));
     P.n0 = n0; P.n1 = n1; P.n2 = n2;
     P.i_begin = p->i_begin; P.i_end = p->i_end;
@@ -145,7 +150,7 @@ static int enqueue_slab(iwb_handle* h, Scratch& c, const iwb_params3d* p, double
     P.seg_len = seg_len;
     P.nseg = (planes + seg_len - 1) / seg_len;
     P.nitems = P.nseg * ntiles;
-    double* dc = (double*)c.coords.p;
+    double* dc = (double*)coords.p;
     P.x = dc; P.xx = dc + n0; P.yy = dc + 2 * n0; P.zz = dc + 2 * n0 + n1;
     P.pc = make_phi_const(p->rho, p->sigma, p->v, p->eps, p->sinh_rs, p->cosh_rs);
     P.cx = make_axis_coef(p->dx); P.cy = make_axis_coef(p->dy); P.cz = make_axis_coef(p->dz);
@@ -159,16 +164,31 @@ static int enqueue_slab(iwb_handle* h, Scratch& c, const iwb_params3d* p, double
             P.shell_thr[s] = -1.0;
     }
     const int nfb_total = (n0 + FLUSH - 1) / FLUSH;
-    IWB_CUDA(c.partial.reserve((size_t)nfb_total * ntiles * ROW * sizeof(double)));
-    P.partial = (double*)c.partial.p;
+    IWB_CUDA(partial.reserve((size_t)nfb_total * ntiles * ROW * sizeof(double)));
+    P.partial = (double*)partial.p;
     P.rho_out = rho_dev;
+    L->dtype = p->dtype; L->nshell = p->nshell; L->cfg_id = cfg_id; L->ntiles = ntiles; L->emit = rho_dev != nullptr;
+    L->fb0 = p->i_begin / FLUSH; L->fb1 = (p->i_end + FLUSH - 1) / FLUSH;
+    return IWB_OK;
+}
 
-    cudaError_t e = launch_k3(p->dtype, p->nshell, rho_dev != nullptr, cfg_id, P, h->sm_count, st);
+// Fused kernel + fixed-order tile reduction into rows [fb0, fb1) of `table`; no host<->device copy.
+static int launch_slab(iwb_handle* h, const Launch3& L, double* table, cudaStream_t st)
+{
+    cudaError_t e = launch_k3(L.dtype, L.nshell, L.emit, L.cfg_id, L.P, h->sm_count, st);
     if (e != cudaSuccess) return fail(IWB_ERR_CUDA, std::string("k_energy3d launch: ") + cudaGetErrorString(e));
-    const int fb0 = p->i_begin / FLUSH, fb1 = (p->i_end + FLUSH - 1) / FLUSH;
-    k_reduce_tiles<<<fb1 - fb0, 128, 0, st>>>(P.partial, table, fb0, ntiles);
+    k_reduce_tiles<<<L.fb1 - L.fb0, 128, 0, st>>>(L.P.partial, table, L.fb0, L.ntiles);
     IWB_CUDA(cudaGetLastError());
     return IWB_OK;
+}
+
+static int enqueue_slab(iwb_handle* h, Scratch& c, const iwb_params3d* p, double* table, cudaStream_t st,
+                        double* rho_dev)
+{
+    Launch3 L;
+    int rc = prepare_slab(h, p, c.h_coords, c.coords, c.partial, st, rho_dev, &L);
+    if (rc) return rc;
+    return launch_slab(h, L, table, st);
 }
 
 static void unpack_row(const double* row, int nshell, iwb_result* out)
@@ -215,6 +235,13 @@ static int enqueue_full(iwb_handle* h, Scratch& c, const iwb_params3d* p)
 }
 
 }  // namespace iwb
+
+struct iwb_plan3d {
+    iwb_handle* h = nullptr;
+    iwb::Launch3 L;
+    iwb::DevBuf coords, partial;
+    iwb::PinBuf h_coords;
+};
 
 using namespace iwb;
 
@@ -270,6 +297,47 @@ int iwb_reduce_table(iwb_handle* h, const double* table_device, int nrows, int n
     IWB_CUDA(cudaStreamSynchronize(st));
     memset(out, 0, sizeof(*out));
     unpack_row((const double*)c.h_out.p, nshell, out);
+    return IWB_OK;
+}
+
+int iwb_plan3d_create(iwb_handle* h, const iwb_params3d* p, iwb_plan3d** out)
+{
+    if (!h || !out) return fail(IWB_ERR_INVALID, "iwb_plan3d_create: null argument");
+    *out = nullptr;
+    int rc = validate(p);
+    if (rc) return rc;
+    if (p->rho_out && !p->rho_out_is_device)
+        return fail(IWB_ERR_INVALID, "iwb_plan3d_create: rho_out must be a device pointer (or NULL)");
+    IWB_CUDA(cudaSetDevice(h->device));
+    iwb_plan3d* plan = new iwb_plan3d();
+    plan->h = h;
+    cudaStream_t st = h->scr[0].stream;
+    rc = prepare_slab(h, p, plan->h_coords, plan->coords, plan->partial, st, p->rho_out, &plan->L);
+    if (rc == IWB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(IWB_ERR_CUDA, "iwb_plan3d_create: upload failed");
+    if (rc) {
+        plan->coords.release(); plan->partial.release(); plan->h_coords.release();
+        delete plan;
+        return rc;
+    }
+    *out = plan;
+    return IWB_OK;
+}
+
+int iwb_plan3d_run_async(iwb_plan3d* plan, double* table_device, void* stream)
+{
+    if (!plan || !table_device) return fail(IWB_ERR_INVALID, "iwb_plan3d_run_async: null argument");
+    IWB_CUDA(cudaSetDevice(plan->h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : plan->h->scr[0].stream;
+    return launch_slab(plan->h, plan->L, table_device, st);
+}
+
+int iwb_plan3d_destroy(iwb_plan3d* plan)
+{
+    if (!plan) return IWB_OK;
+    cudaSetDevice(plan->h->device);
+    cudaDeviceSynchronize();
+    plan->coords.release(); plan->partial.release(); plan->h_coords.release();
+    delete plan;
     return IWB_OK;
 }
 

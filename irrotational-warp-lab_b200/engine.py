@@ -120,6 +120,10 @@ class Engine:
                                                       C.c_void_p(int(stream_ptr or 0))))
         return keep
 
+    def plan3d(self, **kw):
+        """Prepared evaluation (coordinates resident on the device); see :class:`Plan3D`."""
+        return Plan3D(self, **kw)
+
     def reduce_table(self, table_ptr, nrows, nshell, stream_ptr=None):
         r = _capi.Result()
         _capi.check(self._lib.iwb_reduce_table(self._h, C.c_void_p(int(table_ptr)), int(nrows), int(nshell),
@@ -180,6 +184,33 @@ class Engine:
         bad = C.c_uint64()
         _capi.check(self._lib.iwb_selftest_constdiv(self._h, float(divisor), int(count), int(seed), C.byref(bad)))
         return bad.value
+
+
+class Plan3D:
+    """``iwb_plan3d``: upload once, launch many times without host<->device copies."""
+
+    def __init__(self, eng: Engine, **kw):
+        self._eng = eng
+        p, self._keep = Engine.make_params3d(**kw)
+        self.nshell = p.nshell
+        self.n0, self.i_begin, self.i_end = p.n0, p.i_begin, p.i_end
+        h = C.c_void_p()
+        _capi.check(eng._lib.iwb_plan3d_create(eng._h, C.byref(p), C.byref(h)))
+        self._h = h
+
+    def run_async(self, table_ptr, stream_ptr=None):
+        _capi.check(self._eng._lib.iwb_plan3d_run_async(self._h, C.c_void_p(int(table_ptr)), C.c_void_p(int(stream_ptr or 0))))
+
+    def close(self):
+        if self._h:
+            self._eng._lib.iwb_plan3d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def get_engine(device: int | None = None) -> Engine:
