@@ -118,7 +118,7 @@ int iwb_energy3d(iwb_handle *h, const iwb_params3d *p, iwb_result *out);
 /* Slab evaluation for the multi-GPU path.  Writes the per-flush-block table
  * rows [i_begin/IWB_FLUSH_PLANES, ceil(i_end/IWB_FLUSH_PLANES)) x IWB_ROW_WIDTH into
  * `table_device` (DEVICE pointer to the full [ceil(n0/IWB_FLUSH_PLANES), IWB_ROW_WIDTH] table; rows of
- * other slabs are not touched) on `stream` (a cudaStream_t passed as void*, NULL = the handle's
+ * other slabs are not touched) on `stream` (a cudaStream_t passed as void*; NULL = CUDA's default
  * stream) WITHOUT synchronising.  i_begin must be a multiple of IWB_FLUSH_PLANES. */
 int iwb_energy3d_slab_async(iwb_handle *h, const iwb_params3d *p, double *table_device, void *stream);
 

@@ -277,7 +277,7 @@ int iwb_energy3d_slab_async(iwb_handle* h, const iwb_params3d* p, double* table_
         return fail(IWB_ERR_INVALID, "iwb_energy3d_slab_async: rho_out must be a device pointer");
     IWB_CUDA(cudaSetDevice(h->device));
     Scratch& c = h->scr[0];
-    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    cudaStream_t st = (cudaStream_t)stream;      // NULL is CUDA's default stream
     // the staging buffer of scratch 0 is reused: make sure the previous upload from it has completed
     IWB_CUDA(cudaStreamSynchronize(st));
     return enqueue_slab(h, c, p, table_device, st, p->rho_out);
@@ -288,7 +288,7 @@ int iwb_reduce_table(iwb_handle* h, const double* table_device, int nrows, int n
     if (!h || !table_device || !out || nrows < 1) return fail(IWB_ERR_INVALID, "iwb_reduce_table: bad argument");
     IWB_CUDA(cudaSetDevice(h->device));
     Scratch& c = h->scr[0];
-    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    cudaStream_t st = (cudaStream_t)stream;      // NULL is CUDA's default stream
     IWB_CUDA(c.out.reserve(ROW_BYTES_MIN));
     IWB_CUDA(c.h_out.reserve(ROW_BYTES_MIN));
     k_reduce_rows<<<1, 128, 0, st>>>(table_device, (double*)c.out.p, nrows);
@@ -327,7 +327,7 @@ int iwb_plan3d_run_async(iwb_plan3d* plan, double* table_device, void* stream)
 {
     if (!plan || !table_device) return fail(IWB_ERR_INVALID, "iwb_plan3d_run_async: null argument");
     IWB_CUDA(cudaSetDevice(plan->h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : plan->h->scr[0].stream;
+    cudaStream_t st = (cudaStream_t)stream;      // NULL is CUDA's default stream
     return launch_slab(plan->h, plan->L, table_device, st);
 }
 
