@@ -180,6 +180,12 @@ int iwb_measure_fma_peak(iwb_handle *h, int use_fp32, double *tflops, double *sm
  * on `count` pseudo-random numerators; returns the number of mismatching results in *mismatches. */
 int iwb_selftest_constdiv(iwb_handle *h, double divisor, uint64_t count, uint64_t seed, uint64_t *mismatches);
 
+/* Test hook: the branch-free division / square-root sequences of the exact kernels against the built-in
+ * IEEE operators on `count` pseudo-random operand pairs (wide_exponents != 0 also exercises the range
+ * check that routes exceptional operands to the built-in sequence; those pairs are counted in *skipped). */
+int iwb_selftest_divsqrt(iwb_handle *h, uint64_t count, uint64_t seed, int wide_exponents, uint64_t *mismatches_div,
+                         uint64_t *mismatches_sqrt, uint64_t *skipped);
+
 #ifdef __cplusplus
 }
 #endif

@@ -99,6 +99,8 @@ SYMBOLS = {
     "iwb_energy_axisym": (C.c_int, [C.c_void_p, C.POINTER(ParamsAxisym), C.POINTER(Result)]),
     "iwb_slice_z0": (C.c_int, [C.c_void_p, C.POINTER(ParamsSlice), C.POINTER(SliceResultC)]),
     "iwb_measure_fma_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "iwb_selftest_divsqrt": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64),
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "iwb_selftest_constdiv": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
 }
 

@@ -102,6 +102,38 @@ __global__ void k_selftest_constdiv(double d, double rd, uint64_t count, uint64_
     if (bad) atomicAdd(mism, bad);
 }
 
+// ---- branch-free division / sqrt self-test ---------------------------------------------------------
+__global__ void k_selftest_divsqrt(uint64_t count, uint64_t seed, int wide, unsigned long long* out)
+{
+    uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long bad_div = 0, bad_sqrt = 0, skipped = 0;
+    for (uint64_t n = tid; n < count; n += stride) {
+        double v[2];
+        for (int k = 0; k < 2; ++k) {
+            uint64_t z = seed + 0x9E3779B97F4A7C15ull * (2 * n + k + 1);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            z ^= z >> 31;
+            uint64_t mant = z & 0x000FFFFFFFFFFFFFull;
+            uint64_t span = wide ? 2046 : 120;
+            uint64_t expo = (wide ? 1 : 1023 - 60) + ((z >> 52) % span);
+            uint64_t sign = z >> 63;
+            v[k] = __longlong_as_double((long long)((sign << 63) | (expo << 52) | mant));
+        }
+        if (exponent_mid_range(v[0]) && exponent_mid_range(v[1])) {
+            if (div_fast(v[0], v[1]) != v[0] / v[1]) ++bad_div;
+        } else ++skipped;
+        const double s = fabs(v[0]);
+        if (exponent_mid_range(s)) {
+            if (sqrt_fast(s) != sqrt(s)) ++bad_sqrt;
+        }
+    }
+    if (bad_div) atomicAdd(out, bad_div);
+    if (bad_sqrt) atomicAdd(out + 1, bad_sqrt);
+    if (skipped) atomicAdd(out + 2, skipped);
+}
+
 }  // namespace iwb
 
 using namespace iwb;
@@ -226,6 +258,24 @@ int iwb_selftest_constdiv(iwb_handle* h, double divisor, uint64_t count, uint64_
     IWB_CUDA(cudaMemcpyAsync(&bad, c.out.p, 8, cudaMemcpyDeviceToHost, c.stream));
     IWB_CUDA(cudaStreamSynchronize(c.stream));
     *mismatches = bad;
+    return IWB_OK;
+}
+
+int iwb_selftest_divsqrt(iwb_handle* h, uint64_t count, uint64_t seed, int wide_exponents, uint64_t* mismatches_div,
+                         uint64_t* mismatches_sqrt, uint64_t* skipped)
+{
+    if (!h || !mismatches_div || !mismatches_sqrt) return fail(IWB_ERR_INVALID, "iwb_selftest_divsqrt: null argument");
+    IWB_CUDA(cudaSetDevice(h->device));
+    Scratch& c = h->scr[0];
+    IWB_CUDA(c.out.reserve(ROW_BYTES_MIN));
+    IWB_CUDA(cudaMemsetAsync(c.out.p, 0, 24, c.stream));
+    k_selftest_divsqrt<<<h->sm_count * 8, 256, 0, c.stream>>>(count, seed, wide_exponents, (unsigned long long*)c.out.p);
+    IWB_CUDA(cudaGetLastError());
+    unsigned long long res[3] = {0, 0, 0};
+    IWB_CUDA(cudaMemcpyAsync(res, c.out.p, 24, cudaMemcpyDeviceToHost, c.stream));
+    IWB_CUDA(cudaStreamSynchronize(c.stream));
+    *mismatches_div = res[0]; *mismatches_sqrt = res[1];
+    if (skipped) *skipped = res[2];
     return IWB_OK;
 }
 

@@ -180,6 +180,12 @@ class Engine:
         _capi.check(self._lib.iwb_measure_fma_peak(self._h, 1 if fp32 else 0, C.byref(t), C.byref(mhz)))
         return {"tflops": t.value, "sm_mhz_effective": mhz.value}
 
+    def selftest_divsqrt(self, count=1 << 26, seed=1, wide=False):
+        bd, bs, sk = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _capi.check(self._lib.iwb_selftest_divsqrt(self._h, int(count), int(seed), 1 if wide else 0,
+                                                   C.byref(bd), C.byref(bs), C.byref(sk)))
+        return {"div_mismatches": bd.value, "sqrt_mismatches": bs.value, "skipped": sk.value}
+
     def selftest_constdiv(self, divisor, count=1 << 26, seed=1):
         bad = C.c_uint64()
         _capi.check(self._lib.iwb_selftest_constdiv(self._h, float(divisor), int(count), int(seed), C.byref(bad)))
