@@ -28,7 +28,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=o
 # translation unit -> extra flags
 UNITS = {
     "core.cu": [],
-    "energy3d.cu": ["-fmad=false"],
+    "energy3d.cu": ["-fmad=false"] + ([f"-DIWB_DBG={os.environ['IWB_DBG']}"] if os.environ.get("IWB_DBG") else []),
     "planar.cu": ["-fmad=false"],
 }
 

@@ -15,14 +15,14 @@
 namespace iwb {
 
 // ---- kernel geometry variants -----------------------------------------------------------------
-//   config 0: region 32 x 64, 16 warps, 1 CTA / SM (default)
-//   config 1: region 48 x 64, 16 warps, 1 CTA / SM
-//   config 2: region 24 x 64,  8 warps, 2 CTAs / SM
-//   config 3: region 40 x 64, 20 warps, 1 CTA / SM
-// Only the headline variant (float64, <= 2 shells, no rho emission) is built for the experimental
-// configs; every other variant uses config 0.
+//   config 0: region 32 x 64, 16 warps (180 KB smem)      -- built for every variant
+//   config 1: region 40 x 64, 20 warps (225 KB smem)
+//   config 2: region 36 x 64, 18 warps (203 KB smem)
+//   config 3: region 32 x 64,  8 warps
+// Only the headline variant (float64, <= 2 shells, no rho emission) is built for configs > 0;
+// every other variant uses config 0.  One CTA per SM in all of them.
 struct K3Config { int rj, nw; };
-static const K3Config kConfigs[] = {{32, 16}, {48, 16}, {24, 8}, {40, 20}};
+static const K3Config kConfigs[] = {{32, 16}, {40, 20}, {36, 18}, {32, 8}};
 constexpr int kNumConfigs = 4;
 
 template <int DT, int NSH, int RJ, int NW, bool EMIT, int MINB>
@@ -53,9 +53,9 @@ static cudaError_t launch_cfg(int cfg, const K3Params& P, int sm_count, cudaStre
 {
     if (DT == IWB_F64 && NSH == 2 && !EMIT) {
         switch (cfg) {
-        case 1: return launch_one<IWB_F64, 2, 48, 16, false, 1>(P, sm_count, st);
-        case 2: return launch_one<IWB_F64, 2, 24, 8, false, 2>(P, sm_count, st);
-        case 3: return launch_one<IWB_F64, 2, 40, 20, false, 1>(P, sm_count, st);
+        case 1: return launch_one<IWB_F64, 2, 40, 20, false, 1>(P, sm_count, st);
+        case 2: return launch_one<IWB_F64, 2, 36, 18, false, 1>(P, sm_count, st);
+        case 3: return launch_one<IWB_F64, 2, 32, 8, false, 1>(P, sm_count, st);
         default: break;
         }
     }

@@ -10,24 +10,33 @@
 // The CTA's region is the tile plus a 2-point halo: RJ rows (j) x 64 columns (k),
 // lanes along k.  Warp w owns region rows jr = w, w+NW, ...; lane tx owns columns tx, tx+32.
 //
-// Shared memory (doubles, RJ x 64 each):   phi ring [3]   planes p-2, p-1, p
-//                                           phi_x ring [3] planes of d(phi)/dx
-//                                           phi_y, phi_z   of the current output plane
-// Per output plane i:   phase 1: phi(i+2), phi_x(i+1) (own columns) and phi_y(i), phi_z(i)
-//                                from the phi(i) plane                      | __syncthreads
-//                       phase 2: second derivatives, rho, predicated sums   | __syncthreads
-// The row loops are deliberately NOT unrolled (two columns of ILP per thread, 16 warps per SM
-// for latency hiding): the IEEE division / sqrt sequences are long and an unrolled body
-// overflows the instruction cache.
-// Sums are kept in registers and flushed (warp shuffle + fixed-order block tree) once
-// per IWB_FLUSH_PLANES planes into partial[flush block][tile][row]; a second kernel adds
-// the tiles in fixed order.  Flush blocks are aligned to the GLOBAL plane index, so the
-// result is bit-identical for any slab decomposition along i.
+// Shared memory, 11 planes of RJ x 64 doubles:
+//     phi ring [3]   (plane q in slot q mod 3)
+//     phi_x ring [4] (plane q in slot q mod 4)
+//     phi_y, phi_z   double-buffered (plane q in buffer q mod 2)
+// The rings are sized so that ONE barrier per output plane suffices.  Between two barriers every
+// warp runs three mutually independent tasks, for output plane i:
+//     P(i+3): evaluate phi(i+3) at the own columns and finish phi_x(i+2)      -- FP64 heavy, ~no smem
+//     C(i+1): phi_y(i+1), phi_z(i+1) from the phi(i+1) plane                  -- smem heavy
+//     O(i)  : second derivatives, rho, predicated sums of plane i             -- smem heavy, then FP64
+// Half of the warps of every scheduler run them in the order P, C, O and the other half O, C, P, so
+// that shared-memory wavefronts and FP64 issue slots are demanded at the same time instead of in
+// alternating bursts (measured: the two costs are nearly equal and used to add up).
+// Row loops are deliberately NOT unrolled (two columns of ILP per thread): the IEEE division / sqrt
+// sequences are long and an unrolled body overflows the instruction cache.
+// Sums are kept in registers and flushed (warp shuffle + fixed-order block tree) once per
+// IWB_FLUSH_PLANES planes into partial[flush block][tile][row]; a second kernel adds the tiles in
+// fixed order.  Flush blocks are aligned to the GLOBAL plane index, so the result is bit-identical
+// for any slab decomposition along i.
 #pragma once
 #include <type_traits>
 
 #include "iwb_device.cuh"
 #include "../../include/iwb200.h"
+
+#ifndef IWB_DBG
+#define IWB_DBG 0      // development only: 1 = skip task O, 2 = skip the phi evaluation, 3 = both
+#endif
 
 namespace iwb {
 
@@ -35,7 +44,8 @@ constexpr int RK = 64;              // region columns (k): two per lane
 constexpr int TK_MAX = RK - 4;      // tile columns
 constexpr int ROW = IWB_ROW_WIDTH;  // doubles per partial row
 constexpr int FLUSH = IWB_FLUSH_PLANES;
-constexpr int SMEM_PAD = 2 * RK;    // guard doubles before and after the planes (halo reads of edge lanes)
+constexpr int SMEM_PAD = 8;         // guard doubles before and after the planes (lane 0 / lane 31 reads of idx -+ 1)
+constexpr int NPLANES = 11;
 
 struct K3Params {
     int n0, n1, n2;
@@ -62,7 +72,8 @@ struct Geo {
     static constexpr int PLANE = RJ * RK;
     static constexpr int TJ_MAX = RJ - 4;
     static constexpr int NT = NW * 32;
-    static constexpr size_t SMEM_BYTES = (size_t(8) * PLANE + 2 * SMEM_PAD + RJ) * sizeof(double);
+    static constexpr int SCRATCH = NW * ROW;     // block-reduction scratch (doubles)
+    static constexpr size_t SMEM_BYTES = (size_t(NPLANES) * PLANE + 2 * SMEM_PAD + RJ + SCRATCH) * sizeof(double);
 };
 
 template <int DT, int NSH, int RJ, int NW, bool EMIT, int MINB = 1>
@@ -73,14 +84,16 @@ k_energy3d(const __grid_constant__ K3Params P)
     constexpr int PLANE = G::PLANE;
     constexpr int NSHA = NSH > 0 ? NSH : 1;
     extern __shared__ double smem_raw[];
-    double* const phi_ring = smem_raw + SMEM_PAD;
-    double* const px_ring = phi_ring + 3 * PLANE;
-    double* const py_buf = phi_ring + 6 * PLANE;
-    double* const pz_buf = phi_ring + 7 * PLANE;
-    double* const yy_s = phi_ring + 8 * PLANE + SMEM_PAD;   // [RJ] y*y of the region rows
+    double* const phi_ring = smem_raw + SMEM_PAD;          // 3 planes
+    double* const px_ring = phi_ring + 3 * PLANE;          // 4 planes
+    double* const py_buf = phi_ring + 7 * PLANE;           // 2 planes
+    double* const pz_buf = phi_ring + 9 * PLANE;           // 2 planes
+    double* const yy_s = phi_ring + NPLANES * PLANE + SMEM_PAD;   // [RJ] y*y of the region rows
+    double* const scratch = yy_s + RJ;                     // [NW][ROW]
 
     const int tx = threadIdx.x & 31;
     const int ty = threadIdx.x >> 5;
+    const bool order_pco = ((ty >> 2) & 1) == 0;           // task order of this warp (see header)
     const int ntiles = P.ntj * P.ntk;
     const AxisCoef cx = P.cx, cy = P.cy, cz = P.cz;
     const PhiConst pc = P.pc;
@@ -98,6 +111,7 @@ k_energy3d(const __grid_constant__ K3Params P)
         // j == n1-1 is region row Tj+1 of a high-edge tile
         const bool t_jlo = (j0 == 0), t_jhi = (j0 + Tj == P.n1);
         const bool t_kedge = (k0 == 0) || (k0 + Tk == P.n2);
+        const bool tile_edge = t_jlo || t_jhi || t_kedge;
         const int jr_lo = t_jlo ? 2 : 0, jr_hi = t_jhi ? Tj + 1 : Tj + 3;
         const int py_lo = max(jr_lo, 1), py_hi = min(jr_hi, Tj + 2);
 
@@ -146,88 +160,83 @@ k_energy3d(const __grid_constant__ K3Params P)
             return cdiv(B[idx + RK] - B[idx - RK], cy.h2, cy.rh2);
         };
 
-        // ---- phase 1 -----------------------------------------------------------------------
-        // p >= 0: produce phi(p) and the x-derivative it completes (own columns only).
-        // ip >= 0: phi_y(ip), phi_z(ip) from the phi(ip) plane (reads neighbours' columns).
-        auto phase1 = [&](int p, int ip, auto edge_tag) {
+        // ---- task P(p): phi(p) at the own columns, and the x-derivative it completes -----------------
+        // phi_x(p-1) = (phi(p) - phi(p-2)) / 2dx needs phi(p-2) of the own column only.
+        auto taskP = [&](int p, auto edge_tag) {
             constexpr bool EDGE = decltype(edge_tag)::value;
-            double xp = 0.0, xxp = 0.0;
-            double* ph_p = phi_ring;
-            const double *ph_m1 = phi_ring, *ph_m2 = phi_ring;
-            double* px_w = px_ring;
-            bool do_px = false, do_px0 = false;
-            if (p >= 0) {
-                xp = P.x[p]; xxp = P.xx[p];
-                ph_p = phi_ring + (p % 3) * PLANE;
-                ph_m1 = phi_ring + ((p + 2) % 3) * PLANE;      // plane p-1
-                ph_m2 = phi_ring + ((p + 1) % 3) * PLANE;      // plane p-2
-                px_w = px_ring + ((p + 2) % 3) * PLANE;        // phi_x(p-1)
-                do_px = (p - 2 >= pstart);                     // interior formula
-                do_px0 = EDGE && (p == 2) && (pstart == 0);    // phi_x(0), one-sided
-            }
-            const double* const ph_i = phi_ring + ((ip >= 0 ? ip : 0) % 3) * PLANE;
+            const double xp = P.x[p], xxp = P.xx[p];
+            double* const ph_p = phi_ring + (p % 3) * PLANE;
+            const double* const ph_m1 = phi_ring + ((p + 2) % 3) * PLANE;      // plane p-1
+            const double* const ph_m2 = phi_ring + ((p + 1) % 3) * PLANE;      // plane p-2
+            double* const px_w = px_ring + ((p + 3) % 4) * PLANE;              // phi_x(p-1)
+            const bool do_px = (p - 2 >= pstart);                              // interior formula
+            const bool do_px0 = EDGE && (p == 2) && (pstart == 0);             // phi_x(0), one-sided
 #pragma unroll 1
-            for (int jr = ty; jr <= jr_hi; jr += NW) {
-                if (jr < jr_lo) continue;
+            for (int jr = jr_lo + ty; jr <= jr_hi; jr += NW) {
                 const int base = jr * RK + tx;
-                if (p >= 0) {
-                    double f[2];
-                    if (DT == IWB_F64) {
-                        const double sxy = xxp + yy_s[jr];
-                        const double s[2] = {sxy + zz0, sxy + zz1};
-                        phi_exact_f64<2>(s, xp, pc, f);
-                    } else {
-                        const float sxy = __fadd_rn((float)xxp, (float)yy_s[jr]);
-                        const float s[2] = {__fadd_rn(sxy, (float)zz0), __fadd_rn(sxy, (float)zz1)};
-                        phi_exact_f32ref<2>(s, (float)xp, pc, f);
-                    }
-                    ph_p[base] = f[0];
-                    ph_p[base + 32] = f[1];
-                    if (do_px) {
-                        px_w[base] = cdiv(f[0] - ph_m2[base], cx.h2, cx.rh2);
-                        px_w[base + 32] = cdiv(f[1] - ph_m2[base + 32], cx.h2, cx.rh2);
-                    }
-                    if (EDGE && do_px0) {
-                        px_ring[base] = edge3(cx.a0, ph_m2[base], cx.b0, ph_m1[base], cx.c0, f[0]);
-                        px_ring[base + 32] = edge3(cx.a0, ph_m2[base + 32], cx.b0, ph_m1[base + 32], cx.c0, f[1]);
-                    }
+                double f[2];
+                if (IWB_DBG & 2) { f[0] = xxp + zz0; f[1] = xxp + zz1; }
+                else if (DT == IWB_F64) {
+                    const double sxy = xxp + yy_s[jr];
+                    const double s[2] = {sxy + zz0, sxy + zz1};
+                    phi_exact_f64<2>(s, xp, pc, f);
+                } else {
+                    const float sxy = __fadd_rn((float)xxp, (float)yy_s[jr]);
+                    const float s[2] = {__fadd_rn(sxy, (float)zz0), __fadd_rn(sxy, (float)zz1)};
+                    phi_exact_f32ref<2>(s, (float)xp, pc, f);
                 }
-                if (ip >= 0) {
-                    if (jr >= py_lo && jr <= py_hi) {
-                        const int jedge = EDGE ? ((t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0)) : 0;
-                        py_buf[base] = dY(ph_i, base, jedge, edge_tag);
-                        py_buf[base + 32] = dY(ph_i, base + 32, jedge, edge_tag);
-                    }
-                    if (jr >= 2 && jr <= Tj + 1) {
-                        pz_buf[base] = dZ(ph_i, base, cf0, edge_tag);
-                        pz_buf[base + 32] = dZ(ph_i, base + 32, cf1, edge_tag);
-                    }
+                ph_p[base] = f[0];
+                ph_p[base + 32] = f[1];
+                if (do_px) {
+                    px_w[base] = cdiv(f[0] - ph_m2[base], cx.h2, cx.rh2);
+                    px_w[base + 32] = cdiv(f[1] - ph_m2[base + 32], cx.h2, cx.rh2);
+                }
+                if (EDGE && do_px0) {
+                    px_ring[base] = edge3(cx.a0, ph_m2[base], cx.b0, ph_m1[base], cx.c0, f[0]);
+                    px_ring[base + 32] = edge3(cx.a0, ph_m2[base + 32], cx.b0, ph_m1[base + 32], cx.c0, f[1]);
                 }
             }
         };
 
-        // ---- phi_x(n0-1), one-sided.  Its ring slot still holds phi_x(n0-4) until plane n0-3 has been
-        //      output, so it is computed separately, once the march reaches plane n0-2 (or at once if n0 == 3).
-        auto produce_px_last = [&]() {
+        // ---- phi_x(n0-1), one-sided, from the last three phi planes (own columns) -----------------------
+        auto taskP_last = [&]() {
             const int p = P.n0 - 1;
             const double* const ph_p = phi_ring + (p % 3) * PLANE;
             const double* const ph_m1 = phi_ring + ((p + 2) % 3) * PLANE;
             const double* const ph_m2 = phi_ring + ((p + 1) % 3) * PLANE;
-            double* const px_w = px_ring + (p % 3) * PLANE;
+            double* const px_w = px_ring + (p % 4) * PLANE;
 #pragma unroll 1
-            for (int jr = ty; jr <= jr_hi; jr += NW) {
-                if (jr < jr_lo) continue;
+            for (int jr = jr_lo + ty; jr <= jr_hi; jr += NW) {
                 const int base = jr * RK + tx;
                 px_w[base] = edge3(cx.a1, ph_m2[base], cx.b1, ph_m1[base], cx.c1, ph_p[base]);
                 px_w[base + 32] = edge3(cx.a1, ph_m2[base + 32], cx.b1, ph_m1[base + 32], cx.c1, ph_p[base + 32]);
             }
         };
 
+        // ---- task C(q): phi_y(q), phi_z(q) from the phi(q) plane (reads neighbours' columns) ------------
+        auto taskC = [&](int q, auto edge_tag) {
+            constexpr bool EDGE = decltype(edge_tag)::value;
+            const double* const ph = phi_ring + (q % 3) * PLANE;
+            double* const py_w = py_buf + (q & 1) * PLANE;
+            double* const pz_w = pz_buf + (q & 1) * PLANE;
+#pragma unroll 1
+            for (int jr = py_lo + ty; jr <= py_hi; jr += NW) {
+                const int base = jr * RK + tx;
+                const int jedge = EDGE ? ((t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0)) : 0;
+                py_w[base] = dY(ph, base, jedge, edge_tag);
+                py_w[base + 32] = dY(ph, base + 32, jedge, edge_tag);
+                if (jr >= 2 && jr <= Tj + 1) {
+                    pz_w[base] = dZ(ph, base, cf0, edge_tag);
+                    pz_w[base + 32] = dZ(ph, base + 32, cf1, edge_tag);
+                }
+            }
+        };
+
         // ---- predicated sums of one row's two points (reproduce_rodal_exact.py:57-61, 220-224) ------
         // NaN points are not counted here: every point is exactly one of pos / neg / zero / NaN, so the
         // host derives cnt_nan from the number of points.  The shell sums are skipped for a warp none of
-        // whose lanes lies inside any shell (adding +0.0 is the identity, so this does not
-        // change a single bit of the result).
+        // whose lanes lies inside any shell (adding +0.0 is the identity, so this does not change a
+        // single bit of the result).
         auto tally2 = [&](const double (&e)[2], double yyj, double xxi) {
             const bool out0 = (cf0 & 16u) != 0, out1 = (cf1 & 16u) != 0;
             const bool p0 = out0 && (e[0] > 0.0), n0 = out0 && (e[0] < 0.0);
@@ -278,12 +287,15 @@ k_energy3d(const __grid_constant__ K3Params P)
             }
         };
 
-        // ---- phase 2: second derivatives, rho, sums at the output columns of plane i ---------
-        auto phase2 = [&](int i, auto edge_tag) {
+        // ---- task O(i): second derivatives, rho, sums at the output columns of plane i --------------------
+        auto taskO = [&](int i, auto edge_tag) {
             constexpr bool EDGE = decltype(edge_tag)::value;
-            const double* const px_i = px_ring + (i % 3) * PLANE;
-            const double* const px_p = px_ring + ((i + 1) % 3) * PLANE;   // phi_x(i+1)   (== slot of i-2)
-            const double* const px_m = px_ring + ((i + 2) % 3) * PLANE;   // phi_x(i-1)
+            const double* const px_i = px_ring + (i % 4) * PLANE;
+            const double* const px_p = px_ring + ((i + 1) % 4) * PLANE;   // phi_x(i+1)
+            const double* const px_m = px_ring + ((i + 3) % 4) * PLANE;   // phi_x(i-1)
+            const double* const px_m2 = px_ring + ((i + 2) % 4) * PLANE;  // phi_x(i-2) (last plane only)
+            const double* const py_r = py_buf + (i & 1) * PLANE;
+            const double* const pz_r = pz_buf + (i & 1) * PLANE;
             const int iedge = EDGE ? ((i == 0) ? 1 : ((i == P.n0 - 1) ? 2 : 0)) : 0;
             const double xxi = P.xx[i];
 #pragma unroll 1
@@ -297,17 +309,17 @@ k_energy3d(const __grid_constant__ K3Params P)
                     const int idx = base + 32 * a;
                     const unsigned cf = a ? cf1 : cf0;
                     double pxx;
-                    if (EDGE && iedge == 1)
-                        pxx = edge3(cx.a0, px_ring[idx], cx.b0, px_ring[PLANE + idx], cx.c0, px_ring[2 * PLANE + idx]);
-                    else if (EDGE && iedge == 2)
-                        pxx = edge3(cx.a1, px_p[idx], cx.b1, px_m[idx], cx.c1, px_i[idx]);   // phi_x(n0-3), (n0-2), (n0-1)
+                    if (EDGE && iedge == 1)        // phi_x(0), (1), (2)
+                        pxx = edge3(cx.a0, px_i[idx], cx.b0, px_p[idx], cx.c0, px_m2[idx]);
+                    else if (EDGE && iedge == 2)   // phi_x(n0-3), (n0-2), (n0-1)
+                        pxx = edge3(cx.a1, px_m2[idx], cx.b1, px_m[idx], cx.c1, px_i[idx]);
                     else
                         pxx = cdiv(px_p[idx] - px_m[idx], cx.h2, cx.rh2);
                     const double pxy = dY(px_i, idx, jedge, edge_tag);
                     const double pxz = dZ(px_i, idx, cf, edge_tag);
-                    const double pyy = dY(py_buf, idx, jedge, edge_tag);
-                    const double pyz = dZ(py_buf, idx, cf, edge_tag);
-                    const double pzz = dZ(pz_buf, idx, cf, edge_tag);
+                    const double pyy = dY(py_r, idx, jedge, edge_tag);
+                    const double pyz = dZ(py_r, idx, cf, edge_tag);
+                    const double pzz = dZ(pz_r, idx, cf, edge_tag);
                     // K_ij = -phi_ij: the sign cancels in K^2 and in K_ij K^ij (reproduce_rodal_exact.py:198-212)
                     const double tr = (pxx + pyy) + pzz;
                     const double diag = (pxx * pxx + pyy * pyy) + pzz * pzz;
@@ -352,7 +364,6 @@ k_energy3d(const __grid_constant__ K3Params P)
                     else vals[q] += o;
                 }
             }
-            double* scratch = pz_buf;           // free after the trailing barrier of phase 2
             if (tx == 0) {
 #pragma unroll
                 for (int q = 0; q < NV; ++q) scratch[ty * NV + q] = vals[q];
@@ -379,45 +390,65 @@ k_energy3d(const __grid_constant__ K3Params P)
                 }
                 P.partial[((size_t)fb * ntiles + tile) * ROW + slot] = acc;
             }
-            __syncthreads();
+            // the scratch is rewritten at the next flush only, at least one step barrier from here
             acc_pos = 0.0; acc_neg = 0.0; c_pos = c_neg = c_zero = 0;
 #pragma unroll
             for (int s = 0; s < NSHA; ++s) { sh_pos[s] = 0.0; sh_neg[s] = 0.0; sh_cnt[s] = 0; }
         };
 
-        // ---- march ------------------------------------------------------------------------
-        __syncthreads();                 // yy_s visible
-        const bool tile_edge = t_jlo || t_jhi || t_kedge;
-        auto run_phase1 = [&](int p, int ip) {
-            if (tile_edge || (p == 2 && pstart == 0)) phase1(p, ip, std::true_type{});
-            else phase1(p, ip, std::false_type{});
+        auto runP = [&](int p) {
+            if (tile_edge || (p == 2 && pstart == 0)) taskP(p, std::true_type{});
+            else taskP(p, std::false_type{});
         };
+        auto runC = [&](int q) {
+            if (tile_edge) taskC(q, std::true_type{});
+            else taskC(q, std::false_type{});
+        };
+        auto runO = [&](int i) {
+            if (IWB_DBG & 1) return;
+            if (tile_edge || i == 0 || i == P.n0 - 1) taskO(i, std::true_type{});
+            else taskO(i, std::false_type{});
+        };
+        // phi_x(n0-1) may be written once every phi plane exists and its ring slot (that of phi_x(n0-5),
+        // last read by O(n0-4)) is dead, i.e. from the step of output plane n0-3 on; it is first needed
+        // by O(n0-2) (n0 == 3: by every plane, and 0 >= n0-3 holds).
+        auto px_last_ok = [&](int i) { return i >= P.n0 - 3; };
+
+        // ---- prologue: everything O(i0) needs ----------------------------------------------------------
+        __syncthreads();                 // yy_s visible
         int produced = pstart - 1;
         bool px_last_done = false;
-        for (int i = i0; i < i1; ++i) {
-            const int target = min(max(i + 2, 3), P.n0 - 1);
-            const int early = min(target, i + 2);
-            if (i == i0) {
-                while (produced < early) run_phase1(++produced, -1);
-                __syncthreads();                     // prologue planes visible to neighbours
-                run_phase1(-1, i);
-            } else if (produced < early) {
-                ++produced;
-                run_phase1(produced, i);             // steady state: phi(i+2) together with phi_y/phi_z(i)
-            } else {
-                run_phase1(-1, i);
-            }
-            if (produced < target) {                 // only i == 0: phi(3) reuses the slot of phi(0)
-                __syncthreads();
-                run_phase1(++produced, -1);
-            }
-            if (!px_last_done && max(i - 1, 0) >= P.n0 - 3 && produced == P.n0 - 1) {
-                produce_px_last();
-                px_last_done = true;
-            }
+        {
+            const int upto = min(i0 + 2, P.n0 - 1);
+            while (produced < upto) runP(++produced);
             __syncthreads();
-            if (tile_edge || i == 0 || i == P.n0 - 1) phase2(i, std::true_type{});
-            else phase2(i, std::false_type{});
+            runC(i0);
+            if (i0 == 0 && P.n0 > 3) {   // O(0) needs phi_x(2), i.e. phi(3), which reuses the slot of phi(0)
+                __syncthreads();
+                runP(++produced);
+            }
+            if (produced == P.n0 - 1 && px_last_ok(i0)) { taskP_last(); px_last_done = true; }
+            __syncthreads();
+        }
+
+        // ---- march: one barrier per output plane -------------------------------------------------------
+        for (int i = i0; i < i1; ++i) {
+            const bool doP = produced < min(i + 3, P.n0 - 1);
+            const bool doL = !doP && !px_last_done && produced == P.n0 - 1 && px_last_ok(i);
+            const bool doC = (i + 1 < i1);
+            if (order_pco) {
+                if (doP) runP(produced + 1);
+                if (doL) taskP_last();
+                if (doC) runC(i + 1);
+                runO(i);
+            } else {
+                runO(i);
+                if (doC) runC(i + 1);
+                if (doP) runP(produced + 1);
+                if (doL) taskP_last();
+            }
+            if (doP) ++produced;
+            if (doL) px_last_done = true;
             __syncthreads();
             if (((i + 1) % FLUSH) == 0 || i == i1 - 1) flush(i / FLUSH);
         }
