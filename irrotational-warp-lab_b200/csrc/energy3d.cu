@@ -106,7 +106,7 @@ struct Launch3 {
 
 // Stages coordinates into `hc` (pinned) -> `dc` (device) on `st` and fills the launch record.
 static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, DevBuf& coords, DevBuf& partial,
-                        cudaStream_t st, double* rho_dev, Launch3* L)
+                        DevBuf& counter, cudaStream_t st, double* rho_dev, Launch3* L)
 {
     const int n0 = p->n0, n1 = p->n1, n2 = p->n2;
     const int cfg_id = config_is_built(h->k3_config, p->dtype, p->nshell, rho_dev != nullptr) ? h->k3_config : 0;
@@ -137,12 +137,15 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
     P.ntk = (n2 + TK_MAX - 1) / TK_MAX;
     const int ntiles = P.ntj * P.ntk;
     const int planes = p->i_end - p->i_begin;
-    // planes per work item: whole slab unless that leaves the GPU under-filled / unbalanced
+    // planes per work item: each item pays a 4-plane phi prologue, so items are as long as the dynamic
+    // schedule allows: <= 128 planes, halved while there are fewer than 12 items per SM, >= 32 planes
+    // (a single flush block only when even that cannot fill the GPU)
     int seg_len = ((planes + FLUSH - 1) / FLUSH) * FLUSH;
     if (h->k3_seg_len > 0) {
         seg_len = ((h->k3_seg_len + FLUSH - 1) / FLUSH) * FLUSH;
     } else {
-        const long long want = 6LL * h->sm_count;       // items for a balanced static schedule
+        if (seg_len > 8 * FLUSH) seg_len = 8 * FLUSH;
+        const long long want = 12LL * h->sm_count;
         while (seg_len > 2 * FLUSH && (long long)ntiles * ((planes + seg_len - 1) / seg_len) < want)
             seg_len = ((seg_len / 2 + FLUSH - 1) / FLUSH) * FLUSH;
         if ((long long)ntiles * ((planes + seg_len - 1) / seg_len) < h->sm_count && seg_len > FLUSH) seg_len = FLUSH;
@@ -167,6 +170,11 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
     IWB_CUDA(partial.reserve((size_t)nfb_total * ntiles * ROW * sizeof(double)));
     P.partial = (double*)partial.p;
     P.rho_out = rho_dev;
+    if (!counter.p) {
+        IWB_CUDA(counter.reserve(256));
+        IWB_CUDA(cudaMemsetAsync(counter.p, 0, 256, st));
+    }
+    P.counter = (unsigned int*)counter.p;
     L->dtype = p->dtype; L->nshell = p->nshell; L->cfg_id = cfg_id; L->ntiles = ntiles; L->emit = rho_dev != nullptr;
     L->fb0 = p->i_begin / FLUSH; L->fb1 = (p->i_end + FLUSH - 1) / FLUSH;
     return IWB_OK;
@@ -177,7 +185,7 @@ static int launch_slab(iwb_handle* h, const Launch3& L, double* table, cudaStrea
 {
     cudaError_t e = launch_k3(L.dtype, L.nshell, L.emit, L.cfg_id, L.P, h->sm_count, st);
     if (e != cudaSuccess) return fail(IWB_ERR_CUDA, std::string("k_energy3d launch: ") + cudaGetErrorString(e));
-    k_reduce_tiles<<<L.fb1 - L.fb0, 128, 0, st>>>(L.P.partial, table, L.fb0, L.ntiles);
+    k_reduce_tiles<<<L.fb1 - L.fb0, 128, 0, st>>>(L.P.partial, table, L.fb0, L.ntiles, L.P.counter);
     IWB_CUDA(cudaGetLastError());
     return IWB_OK;
 }
@@ -186,7 +194,7 @@ static int enqueue_slab(iwb_handle* h, Scratch& c, const iwb_params3d* p, double
                         double* rho_dev)
 {
     Launch3 L;
-    int rc = prepare_slab(h, p, c.h_coords, c.coords, c.partial, st, rho_dev, &L);
+    int rc = prepare_slab(h, p, c.h_coords, c.coords, c.partial, c.counter, st, rho_dev, &L);
     if (rc) return rc;
     return launch_slab(h, L, table, st);
 }
@@ -239,7 +247,7 @@ static int enqueue_full(iwb_handle* h, Scratch& c, const iwb_params3d* p)
 struct iwb_plan3d {
     iwb_handle* h = nullptr;
     iwb::Launch3 L;
-    iwb::DevBuf coords, partial;
+    iwb::DevBuf coords, partial, counter;
     iwb::PinBuf h_coords;
 };
 
@@ -312,10 +320,10 @@ int iwb_plan3d_create(iwb_handle* h, const iwb_params3d* p, iwb_plan3d** out)
     iwb_plan3d* plan = new iwb_plan3d();
     plan->h = h;
     cudaStream_t st = h->scr[0].stream;
-    rc = prepare_slab(h, p, plan->h_coords, plan->coords, plan->partial, st, p->rho_out, &plan->L);
+    rc = prepare_slab(h, p, plan->h_coords, plan->coords, plan->partial, plan->counter, st, p->rho_out, &plan->L);
     if (rc == IWB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(IWB_ERR_CUDA, "iwb_plan3d_create: upload failed");
     if (rc) {
-        plan->coords.release(); plan->partial.release(); plan->h_coords.release();
+        plan->coords.release(); plan->partial.release(); plan->counter.release(); plan->h_coords.release();
         delete plan;
         return rc;
     }
@@ -336,7 +344,7 @@ int iwb_plan3d_destroy(iwb_plan3d* plan)
     if (!plan) return IWB_OK;
     cudaSetDevice(plan->h->device);
     cudaDeviceSynchronize();
-    plan->coords.release(); plan->partial.release(); plan->h_coords.release();
+    plan->coords.release(); plan->partial.release(); plan->counter.release(); plan->h_coords.release();
     delete plan;
     return IWB_OK;
 }

@@ -63,6 +63,7 @@ struct K3Params {
     double shell_thr[IWB_MAX_SHELLS];   // r <= R  <=>  s <= shell_thr (s = r*r before sqrt), see host
     double* partial;               // [nfb_total][ntiles][ROW]
     double* rho_out;               // NULL or [i_end-i_begin][n1][n2]
+    unsigned int* counter;         // dynamic work-item counter (0 at launch; reset by k_reduce_tiles)
 };
 
 __host__ __device__ inline int tile_begin(int t, int nt, int n) { return (int)(((long long)t * n) / nt); }
@@ -98,7 +99,15 @@ k_energy3d(const __grid_constant__ K3Params P)
     const AxisCoef cx = P.cx, cy = P.cy, cz = P.cz;
     const PhiConst pc = P.pc;
 
-    for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+    __shared__ int s_item;
+    for (;;) {
+        // dynamic schedule: items are handed out in index order; their partial sums go to fixed slots,
+        // so the result does not depend on which CTA ran which item
+        __syncthreads();                 // previous item's shared memory (and s_item) is dead
+        if (threadIdx.x == 0) s_item = (int)atomicAdd(P.counter, 1u);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= P.nitems) break;
         const int seg = item / ntiles;
         const int tile = item - seg * ntiles;
         const int tj = tile / P.ntk, tk = tile - tj * P.ntk;
@@ -115,7 +124,6 @@ k_energy3d(const __grid_constant__ K3Params P)
         const int jr_lo = t_jlo ? 2 : 0, jr_hi = t_jhi ? Tj + 1 : Tj + 3;
         const int py_lo = max(jr_lo, 1), py_hi = min(jr_hi, Tj + 2);
 
-        __syncthreads();                 // previous item's shared memory is dead
         if (threadIdx.x < RJ) yy_s[threadIdx.x] = P.yy[min(max(j0 - 2 + (int)threadIdx.x, 0), P.n1 - 1)];
 
         // this lane's two columns
@@ -458,8 +466,10 @@ k_energy3d(const __grid_constant__ K3Params P)
 // ---- fixed-order sum over tiles: partial[fb][tile][ROW] -> table[fb][ROW] ----------------------
 // (static: every translation unit that includes this header gets its own copy)
 static __global__ void __launch_bounds__(128) k_reduce_tiles(const double* __restrict__ partial,
-                                                             double* __restrict__ table, int fb_begin, int ntiles)
+                                                             double* __restrict__ table, int fb_begin, int ntiles,
+                                                             unsigned int* counter = nullptr)
 {
+    if (counter && blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;    // re-arm the work queue of k_energy3d
     const int fb = fb_begin + blockIdx.x;
     const int q = threadIdx.x;            // one thread per row slot
     if (q >= ROW) return;

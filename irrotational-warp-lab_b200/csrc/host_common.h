@@ -58,6 +58,7 @@ struct Scratch {
     DevBuf table;      // [nfb][ROW]
     DevBuf out;        // [ROW]
     DevBuf rho;        // staging for a host rho_out
+    DevBuf counter;    // dynamic work-item counter of k_energy3d
     PinBuf h_coords;
     PinBuf h_out;      // [ROW]
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
