@@ -1,0 +1,164 @@
+"""Command-line front ends with the reference's flags and JSON schemas, running on the engine.
+
+  * ``reproduce``  <- ``scripts/reproduce_rodal_exact.py`` ``main``  (/root/reference/scripts/reproduce_rodal_exact.py:244-341)
+  * ``sweep``      <- ``scripts/sweep_superluminal.py`` ``main``     (/root/reference/scripts/sweep_superluminal.py:124-200)
+
+    python -m irrotational_warp_lab_b200.cli reproduce --mode 3d --n 256 --out results/repro.json
+    python -m irrotational_warp_lab_b200.cli sweep --mode 3d --n 80 --v-steps 20 --out results/sweep.json
+
+The payloads keep the reference's keys (``meta, params, run, tail_2pt, wall_clock_s`` and
+``meta, sweep, total_time_s``), so ``convergence_study_3d.py``, ``plot_superluminal.py``,
+``make_paper_figures.py`` and the notebook consume them unchanged; ``run`` gains ``counts`` and ``engine``.
+``--backend`` accepts only ``b200`` here (the NumPy / CuPy paths live in the reference).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+from datetime import datetime, timezone
+
+from . import backend as b200
+from . import sweeps
+
+
+def _git_info() -> dict:
+    try:
+        run = lambda *a: subprocess.check_output(a, stderr=subprocess.DEVNULL).decode("utf-8").strip()
+        sha = run("git", "rev-parse", "HEAD")
+        branch = run("git", "rev-parse", "--abbrev-ref", "HEAD")
+        dirty = subprocess.call(["git", "diff", "--quiet"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) != 0
+        return {"sha": sha, "branch": branch, "dirty": dirty}
+    except Exception:
+        return {"sha": None, "branch": None, "dirty": None}
+
+
+def _write_json(path: str, payload: dict) -> None:
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    with open(path, "w", encoding="utf-8") as f:
+        json.dump(payload, f, indent=2, sort_keys=True)
+
+
+def _shell_summary(e_pos, e_neg):
+    return {"e_pos": e_pos, "e_neg": e_neg, "e_net": float(e_pos + e_neg), **b200.summary_metrics(e_pos, e_neg)}
+
+
+def reproduce_main(argv=None) -> int:
+    p = argparse.ArgumentParser(description="Reproduce Rodal (2025) irrotational energetics on the B200 engine.")
+    p.add_argument("--mode", choices=["axisym", "3d"], default="axisym")
+    p.add_argument("--backend", choices=["b200"], default="b200")
+    p.add_argument("--dtype", choices=["float64", "float32"], default="float64")
+    p.add_argument("--rho", type=float, default=5.0)
+    p.add_argument("--sigma", type=float, default=4.0)
+    p.add_argument("--v", type=float, default=1.0)
+    p.add_argument("--extent-mult", type=float, default=12.0)
+    p.add_argument("--extent-pad", type=float, default=1.1)
+    p.add_argument("--nx", type=int, default=2400, help="axisym: x grid points")
+    p.add_argument("--ny", type=int, default=1200, help="axisym: y grid points")
+    p.add_argument("--n", type=int, default=100, help="3d: points per axis")
+    p.add_argument("--tail-r1-mult", type=float, default=8.0)
+    p.add_argument("--tail-r2-mult", type=float, default=12.0)
+    p.add_argument("--out", type=str, default=None, help="Write JSON summary to this path")
+    args = p.parse_args(argv)
+
+    extent = args.extent_mult * args.rho * args.extent_pad
+    r1 = args.tail_r1_mult * args.rho
+    r2 = args.tail_r2_mult * args.rho
+    if r2 <= r1:
+        raise ValueError("tail-r2-mult must be > tail-r1-mult")
+
+    started = time.perf_counter()
+    if args.mode == "axisym":
+        run = b200.compute_energy_axisymmetric(rho=args.rho, sigma=args.sigma, v=args.v, extent=extent, nx=args.nx,
+                                               ny=args.ny, backend=args.backend, dtype=args.dtype, shells=[r1, r2])
+    else:
+        run = b200.compute_energy_3d(rho=args.rho, sigma=args.sigma, v=args.v, extent=extent, n=args.n,
+                                     backend=args.backend, dtype=args.dtype, shells=[r1, r2])
+    e_at_r = run.pop("_e_at_r")
+    e_pos_r1, e_neg_r1 = e_at_r(r1)
+    e_pos_r2, e_neg_r2 = e_at_r(r2)
+    e_pos_inf = b200.two_point_tail_extrapolation(e_pos_r1, e_pos_r2, r1, r2)
+    e_neg_inf = b200.two_point_tail_extrapolation(e_neg_r1, e_neg_r2, r1, r2)
+    run["counts"]["shell_points"] = {str(k): v for k, v in run["counts"]["shell_points"].items()}
+    tail = {"r1": r1, "r2": r2, "at_r1": _shell_summary(e_pos_r1, e_neg_r1), "at_r2": _shell_summary(e_pos_r2, e_neg_r2),
+            "at_inf": _shell_summary(e_pos_inf, e_neg_inf)}
+    payload = {
+        "meta": {"timestamp_utc": datetime.now(timezone.utc).isoformat(), "git": _git_info(), "python": sys.version},
+        "params": {"rho": args.rho, "sigma": args.sigma, "v": args.v},
+        "run": run,
+        "tail_2pt": tail,
+        "wall_clock_s": float(time.perf_counter() - started),
+    }
+    print("-" * 60)
+    print(f"Mode: {args.mode}")
+    print(f"Params: rho={args.rho}, sigma={args.sigma}, v={args.v}")
+    if args.mode == "axisym":
+        print(f"Grid: nx={run['grid']['nx']}, ny={run['grid']['ny']}, extent={run['grid']['extent']}")
+    else:
+        print(f"Grid: n={run['grid']['n']}, extent={run['grid']['extent']}")
+    r2_ratio = tail["at_r2"]["ratio_e_pos_over_abs_e_neg"]
+    inf_abs, inf_net = tail["at_inf"]["e_abs"], tail["at_inf"]["e_net"]
+    # the reference crashes here when e_neg == 0; print n/a instead
+    print(f"At R2={r2:.3f}: ratio E+/|E-| = " + (f"{r2_ratio:.6g}" if r2_ratio is not None else "n/a"))
+    print("Tail net/abs (∞): " + (f"{abs(inf_net) / inf_abs:.6%}" if inf_abs else "n/a"))
+    print("-" * 60)
+    if args.out:
+        _write_json(args.out, payload)
+        print(f"Wrote JSON: {args.out}")
+    return 0
+
+
+def sweep_main(argv=None) -> int:
+    import numpy as np
+    p = argparse.ArgumentParser(description="Superluminal velocity sweep on the B200 engine")
+    p.add_argument("--mode", choices=["axisym", "3d"], default="axisym")
+    p.add_argument("--backend", choices=["b200"], default="b200")
+    p.add_argument("--dtype", choices=["float64", "float32"], default="float64")
+    p.add_argument("--rho", type=float, default=5.0)
+    p.add_argument("--sigma", type=float, default=4.0)
+    p.add_argument("--v-min", type=float, default=1.0)
+    p.add_argument("--v-max", type=float, default=3.0)
+    p.add_argument("--v-steps", type=int, default=20)
+    p.add_argument("--extent-mult", type=float, default=12.0)
+    p.add_argument("--extent-pad", type=float, default=1.1)
+    p.add_argument("--nx", type=int, default=1200)
+    p.add_argument("--ny", type=int, default=600)
+    p.add_argument("--n", type=int, default=80)
+    p.add_argument("--tail-r1-mult", type=float, default=8.0)
+    p.add_argument("--tail-r2-mult", type=float, default=12.0)
+    p.add_argument("--out", type=str, required=True)
+    args = p.parse_args(argv)
+
+    v_values = np.linspace(args.v_min, args.v_max, args.v_steps).tolist()
+    extent = args.extent_mult * args.rho * args.extent_pad
+    started = time.perf_counter()
+    sweep_data = sweeps.sweep_velocity(mode=args.mode, rho=args.rho, sigma=args.sigma, v_values=v_values, extent=extent,
+                                       tail_r1_mult=args.tail_r1_mult, tail_r2_mult=args.tail_r2_mult,
+                                       backend=args.backend, dtype=args.dtype, nx=args.nx, ny=args.ny, n=args.n)
+    total_time = time.perf_counter() - started
+    payload = {
+        "meta": {"timestamp_utc": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "git": _git_info(), "python": sys.version},
+        "sweep": sweep_data,
+        "total_time_s": total_time,
+    }
+    if int(os.environ.get("RANK", "0")) == 0:
+        _write_json(args.out, payload)
+        print(f"Sweep completed in {total_time:.1f}s; results written to: {args.out}")
+    return 0
+
+
+def main(argv=None) -> int:
+    argv = sys.argv[1:] if argv is None else argv
+    if argv and argv[0] == "reproduce":
+        return reproduce_main(argv[1:])
+    if argv and argv[0] == "sweep":
+        return sweep_main(argv[1:])
+    print("usage: python -m irrotational_warp_lab_b200.cli {reproduce|sweep} [options]", file=sys.stderr)
+    return 2
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
