@@ -22,8 +22,8 @@ namespace iwb {
 // Only the headline variant (float64, <= 2 shells, no rho emission) is built for configs > 0;
 // every other variant uses config 0.  One CTA per SM in all of them.
 struct K3Config { int rj, nw; };
-static const K3Config kConfigs[] = {{32, 16}, {40, 20}, {36, 18}, {32, 8}};
-constexpr int kNumConfigs = 4;
+static const K3Config kConfigs[] = {{32, 16}, {40, 20}, {36, 18}, {32, 8}, {20, 10}, {20, 5}};
+constexpr int kNumConfigs = 6;
 
 template <int DT, int NSH, int RJ, int NW, bool EMIT, int MINB>
 static cudaError_t launch_one(const K3Params& P, int sm_count, cudaStream_t st)
@@ -56,6 +56,8 @@ static cudaError_t launch_cfg(int cfg, const K3Params& P, int sm_count, cudaStre
         case 1: return launch_one<IWB_F64, 2, 40, 20, false, 1>(P, sm_count, st);
         case 2: return launch_one<IWB_F64, 2, 36, 18, false, 1>(P, sm_count, st);
         case 3: return launch_one<IWB_F64, 2, 32, 8, false, 1>(P, sm_count, st);
+        case 4: return launch_one<IWB_F64, 2, 20, 10, false, 2>(P, sm_count, st);
+        case 5: return launch_one<IWB_F64, 2, 20, 5, false, 2>(P, sm_count, st);
         default: break;
         }
     }

@@ -14,14 +14,17 @@
 //     phi ring [3]   (plane q in slot q mod 3)
 //     phi_x ring [4] (plane q in slot q mod 4)
 //     phi_y, phi_z   double-buffered (plane q in buffer q mod 2)
-// The rings are sized so that ONE barrier per output plane suffices.  Between two barriers every
-// warp runs three mutually independent tasks, for output plane i:
-//     P(i+3): evaluate phi(i+3) at the own columns and finish phi_x(i+2)      -- FP64 heavy, ~no smem
-//     C(i+1): phi_y(i+1), phi_z(i+1) from the phi(i+1) plane                  -- smem heavy
+// The rings are sized so that ONE barrier per output plane suffices, and that barrier is split
+// (mbarrier arrive ... wait).  Per output plane i every warp runs
 //     O(i)  : second derivatives, rho, predicated sums of plane i             -- smem heavy, then FP64
-// Half of the warps of every scheduler run them in the order P, C, O and the other half O, C, P, so
-// that shared-memory wavefronts and FP64 issue slots are demanded at the same time instead of in
-// alternating bursts (measured: the two costs are nearly equal and used to add up).
+//     C(i+1): phi_y(i+1), phi_z(i+1) from the phi(i+1) plane                  -- smem heavy
+//     -- arrive --
+//     P(i+3): evaluate phi(i+3) at the own columns and finish phi_x(i+2)      -- FP64 heavy, ~no smem
+//     -- wait --
+// P touches only the own columns' ring entries until two steps later, so it is legal between the
+// arrival and the wait; warps drift apart by up to one task, and the shared-memory-bound tasks of
+// some warps overlap the FP64-bound task of others (measured: 59 -> 77 Gpoints/s over the version
+// with two __syncthreads per plane, whose smem and FP64 phases alternated in lock step).
 // Row loops are deliberately NOT unrolled (two columns of ILP per thread): the IEEE division / sqrt
 // sequences are long and an unrolled body overflows the instruction cache.
 // Sums are kept in registers and flushed (warp shuffle + fixed-order block tree) once per
@@ -94,12 +97,26 @@ k_energy3d(const __grid_constant__ K3Params P)
 
     const int tx = threadIdx.x & 31;
     const int ty = threadIdx.x >> 5;
-    const bool order_pco = ((ty >> 2) & 1) == 0;           // task order of this warp (see header)
     const int ntiles = P.ntj * P.ntk;
     const AxisCoef cx = P.cx, cy = P.cy, cz = P.cz;
     const PhiConst pc = P.pc;
 
     __shared__ int s_item;
+    // Split (arrive / wait) barrier of the march: one mbarrier phase per output plane.
+    __shared__ unsigned long long s_mbar;
+    const unsigned mbar_addr = (unsigned)__cvta_generic_to_shared(&s_mbar);
+    unsigned mbar_parity = 0;
+    if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_addr), "r"(NW * 32));
+    __syncthreads();
+    auto step_arrive = [&]() { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar_addr) : "memory"); };
+    auto step_wait = [&]() {
+        unsigned done;
+        do {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(mbar_addr), "r"(mbar_parity) : "memory");
+        } while (!done);
+        mbar_parity ^= 1u;
+    };
     for (;;) {
         // dynamic schedule: items are handed out in index order; their partial sums go to fixed slots,
         // so the result does not depend on which CTA ran which item
@@ -180,7 +197,8 @@ k_energy3d(const __grid_constant__ K3Params P)
             const bool do_px = (p - 2 >= pstart);                              // interior formula
             const bool do_px0 = EDGE && (p == 2) && (pstart == 0);             // phi_x(0), one-sided
 #pragma unroll 1
-            for (int jr = jr_lo + ty; jr <= jr_hi; jr += NW) {
+            for (int jr = ty; jr <= jr_hi; jr += NW) {        // rows jr == ty (mod NW), as in task O
+                if (jr < jr_lo) continue;
                 const int base = jr * RK + tx;
                 double f[2];
                 if (IWB_DBG & 2) { f[0] = xxp + zz0; f[1] = xxp + zz1; }
@@ -214,7 +232,8 @@ k_energy3d(const __grid_constant__ K3Params P)
             const double* const ph_m2 = phi_ring + ((p + 1) % 3) * PLANE;
             double* const px_w = px_ring + (p % 4) * PLANE;
 #pragma unroll 1
-            for (int jr = jr_lo + ty; jr <= jr_hi; jr += NW) {
+            for (int jr = ty; jr <= jr_hi; jr += NW) {
+                if (jr < jr_lo) continue;
                 const int base = jr * RK + tx;
                 px_w[base] = edge3(cx.a1, ph_m2[base], cx.b1, ph_m1[base], cx.c1, ph_p[base]);
                 px_w[base + 32] = edge3(cx.a1, ph_m2[base + 32], cx.b1, ph_m1[base + 32], cx.c1, ph_p[base + 32]);
@@ -307,7 +326,8 @@ k_energy3d(const __grid_constant__ K3Params P)
             const int iedge = EDGE ? ((i == 0) ? 1 : ((i == P.n0 - 1) ? 2 : 0)) : 0;
             const double xxi = P.xx[i];
 #pragma unroll 1
-            for (int jr = 2 + ty; jr <= Tj + 1; jr += NW) {
+            for (int jr = ty; jr <= Tj + 1; jr += NW) {       // the thread that produced phi_x of a column consumes it
+                if (jr < 2) continue;
                 const int base = jr * RK + tx;
                 const int jedge = EDGE ? ((t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0)) : 0;
                 const double yyj = yy_s[jr];
@@ -441,23 +461,21 @@ k_energy3d(const __grid_constant__ K3Params P)
 
         // ---- march: one barrier per output plane -------------------------------------------------------
         for (int i = i0; i < i1; ++i) {
-            const bool doP = produced < min(i + 3, P.n0 - 1);
+            const bool doP = produced < min(min(i + 3, P.n0 - 1), i1 + 1);   // phi(i1+1) is the last plane this item needs
             const bool doL = !doP && !px_last_done && produced == P.n0 - 1 && px_last_ok(i);
             const bool doC = (i + 1 < i1);
-            if (order_pco) {
-                if (doP) runP(produced + 1);
-                if (doL) taskP_last();
-                if (doC) runC(i + 1);
-                runO(i);
-            } else {
-                runO(i);
-                if (doC) runC(i + 1);
-                if (doP) runP(produced + 1);
-                if (doL) taskP_last();
-            }
+            // What OTHER warps' next step needs from this warp is O(i) (they rewrite the phi_y/phi_z buffer it reads)
+            // and C(i+1) (phi_y/phi_z(i+1) for their O(i+1); phi(i+1) dead for their P(i+4)).  Task P touches only ring
+            // entries of the own columns until two steps later (tasks P and O assign rows to warps identically), so it
+            // runs between the arrival and the wait: the barrier latency and the imbalance of O/C hide behind it.
+            runO(i);
+            if (doC) runC(i + 1);
+            step_arrive();
+            if (doP) runP(produced + 1);
+            if (doL) taskP_last();
+            step_wait();
             if (doP) ++produced;
             if (doL) px_last_done = true;
-            __syncthreads();
             if (((i + 1) % FLUSH) == 0 || i == i1 - 1) flush(i / FLUSH);
         }
     }
