@@ -56,9 +56,45 @@ double shell_threshold_f32(double R)
     return (double)s;
 }
 
+// true when |v| is +0 or 2^lo <= |v| <= 2^hi
+static bool zero_or_in_range(double v, int lo, int hi)
+{
+    if (v == 0.0) return !signbit(v);
+    if (!isfinite(v)) return false;
+    int e;
+    frexp(v, &e);                       // |v| = m * 2^e, m in [0.5, 1)
+    return e - 1 >= lo && e - 1 <= hi;
+}
+
+// Operand-range proof obligations of phi_exact_f64<.., PRECHECKED = true> (iwb_device.cuh).  `zero_index[a]`
+// receives the index of the (single) exactly-zero coordinate of each axis, -1 if none.
+bool phi_fast_path_is_safe(const double* const coords[3], const int n[3], double rho, double sigma, double v, double eps,
+                           double sinh_rs, double cosh_rs, int zero_index[3])
+{
+    bool ok = true;
+    for (int a = 0; a < 3; ++a) {
+        zero_index[a] = -1;
+        for (int i = 0; i < n[a]; ++i) {
+            const double c = coords[a][i];
+            if (!zero_or_in_range(c, -240, 240)) ok = false;
+            if (c == 0.0) {
+                if (zero_index[a] >= 0) ok = false;      // two zeros on one axis: not a linspace, stay general
+                zero_index[a] = i;
+            }
+        }
+    }
+    const double K = (2.0 * sigma) * sinh_rs;
+    if (!isfinite(K) || K == 0.0 || !zero_or_in_range(fabs(K), -150, 150)) ok = false;
+    if (!isfinite(cosh_rs) || !isfinite(rho) || !isfinite(sigma) || !isfinite(v)) ok = false;
+    if (!(eps >= 0.0) || !(eps <= 1.0)) ok = false;
+    if (!(fabs(rho) <= 0x1p200) || !(fabs(sigma) <= 0x1p200) || !(fabs(v) <= 0x1p200)) ok = false;
+    return ok;
+}
+
 PhiConst make_phi_const(double rho, double sigma, double v, double eps, double sinh_rs, double cosh_rs)
 {
     PhiConst c;
+    c.prechecked = 0;
     c.sigma = sigma; c.sigma2 = 2.0 * sigma; c.rho = rho; c.v = v; c.eps = eps;
     c.S = sinh_rs; c.C = cosh_rs;
     c.sigf = (float)sigma; c.sig2f = 2.0f * (float)sigma; c.rhof = (float)rho; c.vf = (float)v; c.epsf = (float)eps;

@@ -158,6 +158,15 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
     double* dc = (double*)coords.p;
     P.x = dc; P.xx = dc + n0; P.yy = dc + 2 * n0; P.zz = dc + 2 * n0 + n1;
     P.pc = make_phi_const(p->rho, p->sigma, p->v, p->eps, p->sinh_rs, p->cosh_rs);
+    {
+        const double* const coords[3] = {p->x, p->y, p->z};
+        const int nn[3] = {n0, n1, n2};
+        int zero_index[3];
+        const bool safe = phi_fast_path_is_safe(coords, nn, p->rho, p->sigma, p->v, p->eps, p->sinh_rs, p->cosh_rs, zero_index);
+        P.pc.prechecked = (safe && p->dtype == IWB_F64) ? 1 : 0;
+        P.i_zero = zero_index[0];
+        P.j_zero = zero_index[1];
+    }
     P.cx = make_axis_coef(p->dx); P.cy = make_axis_coef(p->dy); P.cz = make_axis_coef(p->dz);
     P.dV = (p->dx * p->dy) * p->dz;
     P.c16pi = 16.0 * 3.141592653589793;

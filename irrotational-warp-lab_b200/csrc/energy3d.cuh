@@ -67,6 +67,7 @@ struct K3Params {
     double* partial;               // [nfb_total][ntiles][ROW]
     double* rho_out;               // NULL or [i_end-i_begin][n1][n2]
     unsigned int* counter;         // dynamic work-item counter (0 at launch; reset by k_reduce_tiles)
+    int i_zero, j_zero;            // index of the coordinate that is exactly 0 on axis 0 / 1 (-1: none): r == 0 is possible there
 };
 
 __host__ __device__ inline int tile_begin(int t, int nt, int n) { return (int)(((long long)t * n) / nt); }
@@ -112,8 +113,9 @@ k_energy3d(const __grid_constant__ K3Params P)
     auto step_wait = [&]() {
         unsigned done;
         do {
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(done) : "r"(mbar_addr), "r"(mbar_parity) : "memory");
+            // the suspend-time hint keeps the warp asleep until the phase completes instead of re-polling
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(mbar_addr), "r"(mbar_parity), "r"(1000000u) : "memory");
         } while (!done);
         mbar_parity ^= 1u;
     };
@@ -205,7 +207,10 @@ k_energy3d(const __grid_constant__ K3Params P)
                 else if (DT == IWB_F64) {
                     const double sxy = xxp + yy_s[jr];
                     const double s[2] = {sxy + zz0, sxy + zz1};
-                    phi_exact_f64<2>(s, xp, pc, f);
+                    // the row through the origin (r == 0 at one lane) takes the reference flavour
+                    const bool origin_row = (p == P.i_zero) && (j0 - 2 + jr == P.j_zero);
+                    // (exotic grids / parameters fail the host's operand-range proof: reference flavour throughout)
+                    phi_exact_f64<2, true>(s, xp, pc, f, origin_row || !pc.prechecked);
                 } else {
                     const float sxy = __fadd_rn((float)xxp, (float)yy_s[jr]);
                     const float s[2] = {__fadd_rn(sxy, (float)zz0), __fadd_rn(sxy, (float)zz1)};

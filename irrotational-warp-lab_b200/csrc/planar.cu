@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(AX_NW * 32) k_axisym(const __grid_constant__ A
             double f[1];
             if (DT == IWB_F64) {
                 double s[1] = {xxv[a] + yyv[b]};
-                phi_exact_f64<1>(s, xv[a], P.pc, f);
+                phi_exact_f64<1, false>(s, xv[a], P.pc, f);
             } else {
                 float s[1] = {__fadd_rn((float)xxv[a], (float)yyv[b])};
                 phi_exact_f32ref<1>(s, (float)xv[a], P.pc, f);
