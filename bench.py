@@ -45,6 +45,9 @@ METRIC = "3D Gpoints/s (fp64, n=1024^3)"
 SLOTS_CONTRACT = 271.0
 SLOTS_EXACT_ALG = 114.0
 CPU_SAMPLE_N = 256
+# dram__bytes_read.sum + dram__bytes_write.sum of k_energy3d, one launch at n = 1024^3 on one GPU, from the
+# committed `ncu --set full` capture of this command (profiles/r1_k_energy3d_n1024_final_summary.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = 865024 + 768
 
 
 class ClockSampler:
@@ -292,7 +295,7 @@ def main(argv=None):
             "roofline": {
                 "bound": "fp64", "kernel": "k_energy3d", "unit": "TFLOP/s",
                 "achieved": achieved_exact, "peak": peak["tflops"], "frac": achieved_exact / peak["tflops"],
-                "traffic": None,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (n == 1024 and world == 1) else None,
                 "slots_per_point": SLOTS_EXACT_ALG,
                 "note": "FP64-pipe bound: achieved = kernel points/s x 114 FP64 issue slots/point x 2 (slots of the "
                         "bit-exact algorithm, counted from SASS, DESIGN.md §6); peak = register-resident DFMA "

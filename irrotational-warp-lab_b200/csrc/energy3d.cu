@@ -19,8 +19,9 @@ namespace iwb {
 //   config 1: region 40 x 64, 20 warps (225 KB smem)
 //   config 2: region 36 x 64, 18 warps (203 KB smem)
 //   config 3: region 32 x 64,  8 warps
-// Only the headline variant (float64, <= 2 shells, no rho emission) is built for configs > 0;
-// every other variant uses config 0.  One CTA per SM in all of them.
+// Configs > 1 are experiments built only for the headline variant (float64, <= 2 shells, no rho
+// emission); config 1 (the default) also exists for the float32-reference variant; everything
+// else uses config 0.  Configs 0-3 run one CTA per SM, 4-5 two.
 struct K3Config { int rj, nw; };
 static const K3Config kConfigs[] = {{32, 16}, {40, 20}, {36, 18}, {32, 8}, {20, 10}, {20, 5}};
 constexpr int kNumConfigs = 6;
@@ -45,7 +46,8 @@ static cudaError_t launch_one(const K3Params& P, int sm_count, cudaStream_t st)
 static bool config_is_built(int cfg, int dtype, int nshell, bool emit)
 {
     if (cfg == 0) return true;
-    return cfg > 0 && cfg < kNumConfigs && dtype == IWB_F64 && nshell <= 2 && !emit;
+    if (cfg == 1) return nshell <= 2 && !emit;          // both arithmetic variants
+    return cfg > 1 && cfg < kNumConfigs && dtype == IWB_F64 && nshell <= 2 && !emit;
 }
 
 template <int DT, int NSH, bool EMIT>
@@ -61,6 +63,7 @@ static cudaError_t launch_cfg(int cfg, const K3Params& P, int sm_count, cudaStre
         default: break;
         }
     }
+    if (DT == IWB_F32_REF && NSH == 2 && !EMIT && cfg == 1) return launch_one<IWB_F32_REF, 2, 40, 20, false, 1>(P, sm_count, st);
     return launch_one<DT, NSH, 32, 16, EMIT, 1>(P, sm_count, st);
 }
 

@@ -96,6 +96,11 @@ def all_gather_table(local_rows: "torch.Tensor", n0: int, world_size: int, group
 
     bounds = slab_bounds(n0, world_size)
     counts = [rows_of_slab(a, b)[1] - rows_of_slab(a, b)[0] for a, b in bounds]
+    if min(counts) == max(counts) and counts[0] > 0:
+        # equal slabs (the usual case): the gathered buffer IS the table -- one collective, no extra kernels
+        full = torch.empty((world_size * counts[0], ROW_WIDTH), dtype=torch.float64, device=local_rows.device)
+        dist.all_gather_into_tensor(full.view(-1), local_rows.contiguous().view(-1), group=group)
+        return full
     width = max(max(counts), 1)
     padded = torch.zeros((width, ROW_WIDTH), dtype=torch.float64, device=local_rows.device)
     if local_rows.numel():
