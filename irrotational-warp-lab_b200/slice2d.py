@@ -5,8 +5,8 @@
   * :func:`integrate_signed`  <- ``adm.integrate_signed`` (:91-97)
 
 The tanh-wall dipole potential, the edge_order=1 differences, K_xx/K_yy/K_xy and rho_ADM run in
-``iwb_slice_z0`` (csrc/planar.cu).  ``tail_correction=True`` (an optional host post-process on a
-~100^2 field) is outside the hot path and not provided.
+``iwb_slice_z0`` (csrc/planar.cu).  ``tail_correction=True`` adds the reference's far-field fit as a host
+post-process of the returned rho_adm (``tail.py``; 50 radial bins of a ~100^2 field).
 """
 from __future__ import annotations
 
@@ -36,16 +36,17 @@ class SliceResult:
 def compute_slice_z0(*, rho: float, sigma: float, v: float, extent: float, n: int,
                      tail_correction: bool = False) -> SliceResult:
     """z=0 slice of phi, beta and rho_ADM = (K^2 - K_ij K^ij)/16 pi with the 2x2 K of the slice."""
-    if tail_correction:
-        raise NotImplementedError("tail_correction is a host-side post-process outside the b200 hot path; "
-                                  "apply irrotational_warp.tail.compute_tail_correction to rho_adm")
     x = np.linspace(-extent, extent, n)
     y = np.linspace(-extent, extent, n)
     dx = float(x[1] - x[0])
     dy = float(y[1] - y[0])
     f = get_engine().slice_z0(x=x, y=y, dx=dx, dy=dy, rho=rho, sigma=sigma, v=v)
+    tail = None
+    if tail_correction:                                   # adm.py:73-75
+        from .tail import compute_tail_correction
+        tail = compute_tail_correction(f["rho_adm"], x, y, fit_r_min=0.7 * extent, n_bins=50)
     return SliceResult(x=x, y=y, rho_adm=f["rho_adm"], phi=f["phi"], beta_x=f["beta_x"], beta_y=f["beta_y"],
-                       dx=dx, dy=dy, signed_integrals=(f["pos"], f["neg"], f["net"]))
+                       dx=dx, dy=dy, tail_correction=tail, signed_integrals=(f["pos"], f["neg"], f["net"]))
 
 
 def integrate_signed(field, dx: float, dy: float):

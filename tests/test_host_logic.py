@@ -95,3 +95,27 @@ def test_grid_spacing_is_taken_from_linspace_not_from_the_formula():
     assert dx == 1.3333333333333286 and dx != 132.0 / 99
     x32, dx32 = backend._grid(-66.0, 66.0, 8, "float32")
     assert dx32 == 18.85714340209961 and x32.dtype == np.float32
+
+
+def test_tail_fit_restatement():
+    """Reference tests/test_tail.py restated: constant field averages to itself, a 1/r^4 field is recovered,
+    n <= 2 does not converge; plus a cross-check of the binning against a direct per-bin mean."""
+    from irrotational_warp_lab_b200 import tail
+    x = np.linspace(-10, 10, 101)
+    X, Y = np.meshgrid(x, x)
+    r_bins, avg = tail.radial_average_z0(5.0 * np.ones_like(X), x, x, n_bins=20)
+    assert np.allclose(avg[avg > 0], 5.0, atol=1e-10) and len(r_bins) == 20
+    R = np.sqrt(X ** 2 + Y ** 2) + 1e-6
+    res = tail.compute_tail_correction(2.0 / R ** 4, x, x, n_bins=30)
+    assert abs(res.exponent - 4.0) < 0.1 and res.amplitude > 0 and res.tail_integral_neg == 0.0
+    assert res.tail_integral_pos > 0 and res.tail_uncertainty >= 0 and res.fit_r_max == res.r_bins[-1]
+    assert tail.tail_integral_2d(1.0, 2.0, 10.0) == (0.0, 0.0) and tail.tail_integral_2d(1.0, 1.5, 10.0) == (0.0, 0.0)
+    pos, neg = tail.tail_integral_2d(1.0, 3.0, 10.0)
+    assert abs(pos - 2.0 * np.pi * (1.0 / 10.0)) < 1e-12 and neg == 0.0
+    pos, neg = tail.tail_integral_2d(-1.0, 4.0, 10.0)
+    assert pos == 0.0 and abs(neg - 2.0 * np.pi * (1.0 / (2.0 * 100.0))) < 1e-12
+    assert tail.fit_power_law_decay(np.array([1.0, 2.0]), np.array([1.0, 0.5]), 0.0, 3.0) == (0.0, 0.0, np.inf)
+    # the closed last edge: the farthest point belongs to no bin
+    edges = np.linspace(0, R.max(), 31)
+    sel = (R >= edges[-2]) & (R < edges[-1])
+    assert avg.shape == (20,) and not sel[R == R.max()].any()
