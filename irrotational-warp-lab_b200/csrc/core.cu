@@ -69,14 +69,15 @@ static bool zero_or_in_range(double v, int lo, int hi)
 // Operand-range proof obligations of phi_exact_f64<.., PRECHECKED = true> (iwb_device.cuh).  `zero_index[a]`
 // receives the index of the (single) exactly-zero coordinate of each axis, -1 if none.
 bool phi_fast_path_is_safe(const double* const coords[3], const int n[3], double rho, double sigma, double v, double eps,
-                           double sinh_rs, double cosh_rs, int zero_index[3])
+                           double sinh_rs, double cosh_rs, int zero_index[3], bool float32_grid)
 {
     bool ok = true;
+    const int lim = float32_grid ? 49 : 240;       // |c| in [2^-lim, 2^lim]
     for (int a = 0; a < 3; ++a) {
         zero_index[a] = -1;
         for (int i = 0; i < n[a]; ++i) {
             const double c = coords[a][i];
-            if (!zero_or_in_range(c, -240, 240)) ok = false;
+            if (!zero_or_in_range(c, -lim, lim)) ok = false;
             if (c == 0.0) {
                 if (zero_index[a] >= 0) ok = false;      // two zeros on one axis: not a linspace, stay general
                 zero_index[a] = i;
@@ -87,6 +88,7 @@ bool phi_fast_path_is_safe(const double* const coords[3], const int n[3], double
     if (!isfinite(K) || K == 0.0 || !zero_or_in_range(fabs(K), -150, 150)) ok = false;
     if (!isfinite(cosh_rs) || !isfinite(rho) || !isfinite(sigma) || !isfinite(v)) ok = false;
     if (!(eps >= 0.0) || !(eps <= 1.0)) ok = false;
+    if (float32_grid && !(fabs(rho) <= 0x1p40 && fabs(sigma) <= 0x1p40 && fabs(v) <= 0x1p40 && (eps == 0.0 || eps >= 0x1p-100))) ok = false;
     if (!(fabs(rho) <= 0x1p200) || !(fabs(sigma) <= 0x1p200) || !(fabs(v) <= 0x1p200)) ok = false;
     return ok;
 }
@@ -163,6 +165,14 @@ __global__ void k_selftest_divsqrt(uint64_t count, uint64_t seed, int wide, unsi
         const double s = fabs(v[0]);
         if (exponent_mid_range(s)) {
             if (sqrt_fast(s) != sqrt(s)) ++bad_sqrt;
+        }
+        // float32 flavours on operands derived from the same bits (exponents folded into the guarded range)
+        {
+            const unsigned ua = (unsigned)(__double_as_longlong(v[0]) >> 9), ub = (unsigned)(__double_as_longlong(v[1]) >> 11);
+            const float fa = __int_as_float((ua & 0x807fffffu) | ((77u + (ua >> 23) % 100u) << 23));
+            const float fb = __int_as_float((ub & 0x807fffffu) | ((77u + (ub >> 23) % 100u) << 23));
+            if (divf_fast(fa, fb) != __fdiv_rn(fa, fb)) ++bad_div;
+            if (sqrtf_fast(fabsf(fa)) != __fsqrt_rn(fabsf(fa))) ++bad_sqrt;
         }
     }
     if (bad_div) atomicAdd(out, bad_div);

@@ -165,8 +165,8 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
         const double* const coords[3] = {p->x, p->y, p->z};
         const int nn[3] = {n0, n1, n2};
         int zero_index[3];
-        const bool safe = phi_fast_path_is_safe(coords, nn, p->rho, p->sigma, p->v, p->eps, p->sinh_rs, p->cosh_rs, zero_index);
-        P.pc.prechecked = (safe && p->dtype == IWB_F64) ? 1 : 0;
+        const bool safe = phi_fast_path_is_safe(coords, nn, p->rho, p->sigma, p->v, p->eps, p->sinh_rs, p->cosh_rs, zero_index, p->dtype != IWB_F64);
+        P.pc.prechecked = safe ? 1 : 0;
         P.i_zero = zero_index[0];
         P.j_zero = zero_index[1];
     }

@@ -214,7 +214,8 @@ k_energy3d(const __grid_constant__ K3Params P)
                 } else {
                     const float sxy = __fadd_rn((float)xxp, (float)yy_s[jr]);
                     const float s[2] = {__fadd_rn(sxy, (float)zz0), __fadd_rn(sxy, (float)zz1)};
-                    phi_exact_f32ref<2>(s, (float)xp, pc, f);
+                    const bool origin_row = (p == P.i_zero) && (j0 - 2 + jr == P.j_zero);
+                    phi_exact_f32ref<2, true>(s, (float)xp, pc, f, origin_row || !pc.prechecked);
                 }
                 ph_p[base] = f[0];
                 ph_p[base + 32] = f[1];

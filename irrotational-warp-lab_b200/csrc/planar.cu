@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(AX_NW * 32) k_axisym(const __grid_constant__ A
                 phi_exact_f64<1, false>(s, xv[a], P.pc, f);
             } else {
                 float s[1] = {__fadd_rn((float)xxv[a], (float)yyv[b])};
-                phi_exact_f32ref<1>(s, (float)xv[a], P.pc, f);
+                phi_exact_f32ref<1, false>(s, (float)xv[a], P.pc, f);
             }
             ph[jr_[b] * RK + tx + 32 * a] = f[0];
         }
