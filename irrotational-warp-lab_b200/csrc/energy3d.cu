@@ -15,16 +15,13 @@
 namespace iwb {
 
 // ---- kernel geometry variants -----------------------------------------------------------------
-//   config 0: region 32 x 64, 16 warps (180 KB smem)      -- built for every variant
-//   config 1: region 40 x 64, 20 warps (225 KB smem)
-//   config 2: region 36 x 64, 18 warps (203 KB smem)
-//   config 3: region 32 x 64,  8 warps
-// Configs > 1 are experiments built only for the headline variant (float64, <= 2 shells, no rho
-// emission); config 1 (the default) also exists for the float32-reference variant; everything
-// else uses config 0.  Configs 0-3 run one CTA per SM, 4-5 two.
+//   config 0: region 32 x 64, 16 warps (180 KB smem)  -- built for every variant
+//   config 1: region 40 x 64, 20 warps (225 KB smem)  -- default; built for <= 2 shells without rho emission
+// One CTA per SM.  (Measured alternatives, n = 1024^3 fp64: 36x64/18 warps 72, 32x64/8 warps 52,
+// two CTAs per SM of 20x64/10 warps 64 Gpoints/s against 77 for config 1; profiles/r1_k_energy3d_history.txt.)
 struct K3Config { int rj, nw; };
-static const K3Config kConfigs[] = {{32, 16}, {40, 20}, {36, 18}, {32, 8}, {20, 10}, {20, 5}};
-constexpr int kNumConfigs = 6;
+static const K3Config kConfigs[] = {{32, 16}, {40, 20}};
+constexpr int kNumConfigs = 2;
 
 template <int DT, int NSH, int RJ, int NW, bool EMIT, int MINB>
 static cudaError_t launch_one(const K3Params& P, int sm_count, cudaStream_t st)
@@ -45,25 +42,15 @@ static cudaError_t launch_one(const K3Params& P, int sm_count, cudaStream_t st)
 
 static bool config_is_built(int cfg, int dtype, int nshell, bool emit)
 {
+    (void)dtype;
     if (cfg == 0) return true;
-    if (cfg == 1) return nshell <= 2 && !emit;          // both arithmetic variants
-    return cfg > 1 && cfg < kNumConfigs && dtype == IWB_F64 && nshell <= 2 && !emit;
+    return cfg == 1 && nshell <= 2 && !emit;
 }
 
 template <int DT, int NSH, bool EMIT>
 static cudaError_t launch_cfg(int cfg, const K3Params& P, int sm_count, cudaStream_t st)
 {
-    if (DT == IWB_F64 && NSH == 2 && !EMIT) {
-        switch (cfg) {
-        case 1: return launch_one<IWB_F64, 2, 40, 20, false, 1>(P, sm_count, st);
-        case 2: return launch_one<IWB_F64, 2, 36, 18, false, 1>(P, sm_count, st);
-        case 3: return launch_one<IWB_F64, 2, 32, 8, false, 1>(P, sm_count, st);
-        case 4: return launch_one<IWB_F64, 2, 20, 10, false, 2>(P, sm_count, st);
-        case 5: return launch_one<IWB_F64, 2, 20, 5, false, 2>(P, sm_count, st);
-        default: break;
-        }
-    }
-    if (DT == IWB_F32_REF && NSH == 2 && !EMIT && cfg == 1) return launch_one<IWB_F32_REF, 2, 40, 20, false, 1>(P, sm_count, st);
+    if (NSH == 2 && !EMIT && cfg == 1) return launch_one<DT, 2, 40, 20, false, 1>(P, sm_count, st);
     return launch_one<DT, NSH, 32, 16, EMIT, 1>(P, sm_count, st);
 }
 

@@ -37,6 +37,9 @@
 #include "iwb_device.cuh"
 #include "../../include/iwb200.h"
 
+#ifndef IWB_BARRIER_BACKOFF_NS
+#define IWB_BARRIER_BACKOFF_NS 100
+#endif
 #ifndef IWB_DBG
 #define IWB_DBG 0      // development only: 1 = skip task O, 2 = skip the phi evaluation, 3 = both
 #endif
@@ -112,11 +115,14 @@ k_energy3d(const __grid_constant__ K3Params P)
     auto step_arrive = [&]() { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar_addr) : "memory"); };
     auto step_wait = [&]() {
         unsigned done;
-        do {
-            // the suspend-time hint keeps the warp asleep until the phase completes instead of re-polling
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(done) : "r"(mbar_addr), "r"(mbar_parity), "r"(1000000u) : "memory");
-        } while (!done);
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(mbar_addr), "r"(mbar_parity) : "memory");
+        while (!done) {
+            // back off: a polling warp would otherwise take issue slots from the warps still working
+            __nanosleep(IWB_BARRIER_BACKOFF_NS);
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(mbar_addr), "r"(mbar_parity) : "memory");
+        }
         mbar_parity ^= 1u;
     };
     for (;;) {
