@@ -195,13 +195,13 @@ k_energy3d(const __grid_constant__ K3Params P)
 
         // ---- task P(p): phi(p) at the own columns, and the x-derivative it completes -----------------
         // phi_x(p-1) = (phi(p) - phi(p-2)) / 2dx needs phi(p-2) of the own column only.
-        auto taskP = [&](int p, auto edge_tag) {
+        auto taskP = [&](int p, int s3 /* p mod 3 */, double xp, double xxp, auto edge_tag) {
             constexpr bool EDGE = decltype(edge_tag)::value;
-            const double xp = P.x[p], xxp = P.xx[p];
-            double* const ph_p = phi_ring + (p % 3) * PLANE;
-            const double* const ph_m1 = phi_ring + ((p + 2) % 3) * PLANE;      // plane p-1
-            const double* const ph_m2 = phi_ring + ((p + 1) % 3) * PLANE;      // plane p-2
-            double* const px_w = px_ring + ((p + 3) % 4) * PLANE;              // phi_x(p-1)
+            const int s3m1 = (s3 == 0) ? 2 : s3 - 1, s3m2 = (s3 == 2) ? 0 : s3 + 1;
+            double* const ph_p = phi_ring + s3 * PLANE;
+            const double* const ph_m1 = phi_ring + s3m1 * PLANE;               // plane p-1
+            const double* const ph_m2 = phi_ring + s3m2 * PLANE;               // plane p-2
+            double* const px_w = px_ring + ((p + 3) & 3) * PLANE;              // phi_x(p-1)
             const bool do_px = (p - 2 >= pstart);                              // interior formula
             const bool do_px0 = EDGE && (p == 2) && (pstart == 0);             // phi_x(0), one-sided
 #pragma unroll 1
@@ -253,9 +253,9 @@ k_energy3d(const __grid_constant__ K3Params P)
         };
 
         // ---- task C(q): phi_y(q), phi_z(q) from the phi(q) plane (reads neighbours' columns) ------------
-        auto taskC = [&](int q, auto edge_tag) {
+        auto taskC = [&](int q, int s3 /* q mod 3 */, auto edge_tag) {
             constexpr bool EDGE = decltype(edge_tag)::value;
-            const double* const ph = phi_ring + (q % 3) * PLANE;
+            const double* const ph = phi_ring + s3 * PLANE;
             double* const py_w = py_buf + (q & 1) * PLANE;
             double* const pz_w = pz_buf + (q & 1) * PLANE;
 #pragma unroll 1
@@ -327,16 +327,15 @@ k_energy3d(const __grid_constant__ K3Params P)
         };
 
         // ---- task O(i): second derivatives, rho, sums at the output columns of plane i --------------------
-        auto taskO = [&](int i, auto edge_tag) {
+        auto taskO = [&](int i, double xxi, auto edge_tag) {
             constexpr bool EDGE = decltype(edge_tag)::value;
-            const double* const px_i = px_ring + (i % 4) * PLANE;
-            const double* const px_p = px_ring + ((i + 1) % 4) * PLANE;   // phi_x(i+1)
-            const double* const px_m = px_ring + ((i + 3) % 4) * PLANE;   // phi_x(i-1)
-            const double* const px_m2 = px_ring + ((i + 2) % 4) * PLANE;  // phi_x(i-2) (last plane only)
+            const double* const px_i = px_ring + (i & 3) * PLANE;
+            const double* const px_p = px_ring + ((i + 1) & 3) * PLANE;   // phi_x(i+1)
+            const double* const px_m = px_ring + ((i + 3) & 3) * PLANE;   // phi_x(i-1)
+            const double* const px_m2 = px_ring + ((i + 2) & 3) * PLANE;  // phi_x(i-2) (last plane only)
             const double* const py_r = py_buf + (i & 1) * PLANE;
             const double* const pz_r = pz_buf + (i & 1) * PLANE;
             const int iedge = EDGE ? ((i == 0) ? 1 : ((i == P.n0 - 1) ? 2 : 0)) : 0;
-            const double xxi = P.xx[i];
 #pragma unroll 1
             for (int jr = ty; jr <= Tj + 1; jr += NW) {       // the thread that produced phi_x of a column consumes it
                 if (jr < 2) continue;
@@ -436,18 +435,18 @@ k_energy3d(const __grid_constant__ K3Params P)
             for (int s = 0; s < NSHA; ++s) { sh_pos[s] = 0.0; sh_neg[s] = 0.0; sh_cnt[s] = 0; }
         };
 
-        auto runP = [&](int p) {
-            if (tile_edge || (p == 2 && pstart == 0)) taskP(p, std::true_type{});
-            else taskP(p, std::false_type{});
+        auto runP = [&](int p, int s3, double xp, double xxp) {
+            if (tile_edge || (p == 2 && pstart == 0)) taskP(p, s3, xp, xxp, std::true_type{});
+            else taskP(p, s3, xp, xxp, std::false_type{});
         };
-        auto runC = [&](int q) {
-            if (tile_edge) taskC(q, std::true_type{});
-            else taskC(q, std::false_type{});
+        auto runC = [&](int q, int s3) {
+            if (tile_edge) taskC(q, s3, std::true_type{});
+            else taskC(q, s3, std::false_type{});
         };
-        auto runO = [&](int i) {
+        auto runO = [&](int i, double xxi) {
             if (IWB_DBG & 1) return;
-            if (tile_edge || i == 0 || i == P.n0 - 1) taskO(i, std::true_type{});
-            else taskO(i, std::false_type{});
+            if (tile_edge || i == 0 || i == P.n0 - 1) taskO(i, xxi, std::true_type{});
+            else taskO(i, xxi, std::false_type{});
         };
         // phi_x(n0-1) may be written once every phi plane exists and its ring slot (that of phi_x(n0-5),
         // last read by O(n0-4)) is dead, i.e. from the step of output plane n0-3 on; it is first needed
@@ -460,35 +459,47 @@ k_energy3d(const __grid_constant__ K3Params P)
         bool px_last_done = false;
         {
             const int upto = min(i0 + 2, P.n0 - 1);
-            while (produced < upto) runP(++produced);
+            while (produced < upto) { ++produced; runP(produced, produced % 3, P.x[produced], P.xx[produced]); }
             __syncthreads();
-            runC(i0);
+            runC(i0, i0 % 3);
             if (i0 == 0 && P.n0 > 3) {   // O(0) needs phi_x(2), i.e. phi(3), which reuses the slot of phi(0)
                 __syncthreads();
-                runP(++produced);
+                ++produced;
+                runP(produced, produced % 3, P.x[produced], P.xx[produced]);
             }
             if (produced == P.n0 - 1 && px_last_ok(i0)) { taskP_last(); px_last_done = true; }
             __syncthreads();
         }
 
-        // ---- march: one barrier per output plane -------------------------------------------------------
+        // ---- march: one (split) barrier per output plane -----------------------------------------------
+        const int plim = min(P.n0 - 1, i1 + 1);          // phi(i1+1) is the last plane this item needs
+        int m3 = i0 % 3;                                 // i mod 3, kept incrementally (no division in the loop)
         for (int i = i0; i < i1; ++i) {
-            const bool doP = produced < min(min(i + 3, P.n0 - 1), i1 + 1);   // phi(i1+1) is the last plane this item needs
+            const bool doP = produced < min(i + 3, plim);
             const bool doL = !doP && !px_last_done && produced == P.n0 - 1 && px_last_ok(i);
             const bool doC = (i + 1 < i1);
+            // coordinates of this step's planes, requested before the tasks that hide their latency
+            const int pn = min(produced + 1, P.n0 - 1);
+            const double xp_n = P.x[pn], xxp_n = P.xx[pn], xxi = P.xx[i];
+            const int m3p1 = (m3 == 2) ? 0 : m3 + 1;
             // What OTHER warps' next step needs from this warp is O(i) (they rewrite the phi_y/phi_z buffer it reads)
             // and C(i+1) (phi_y/phi_z(i+1) for their O(i+1); phi(i+1) dead for their P(i+4)).  Task P touches only ring
             // entries of the own columns until two steps later (tasks P and O assign rows to warps identically), so it
             // runs between the arrival and the wait: the barrier latency and the imbalance of O/C hide behind it.
-            runO(i);
-            if (doC) runC(i + 1);
+            runO(i, xxi);
+            if (doC) runC(i + 1, m3p1);
             step_arrive();
-            if (doP) runP(produced + 1);
+            if (doP) {
+                // steady state: produced + 1 == i + 3, whose slot is i mod 3; otherwise (start / end of the axis) compute it
+                const int pp = produced + 1;
+                runP(pp, (pp == i + 3) ? m3 : pp % 3, xp_n, xxp_n);
+            }
             if (doL) taskP_last();
             step_wait();
             if (doP) ++produced;
             if (doL) px_last_done = true;
-            if (((i + 1) % FLUSH) == 0 || i == i1 - 1) flush(i / FLUSH);
+            if (((i + 1) & (FLUSH - 1)) == 0 || i == i1 - 1) flush(i / FLUSH);
+            m3 = m3p1;
         }
     }
 }
