@@ -62,7 +62,8 @@ enum iwb_dtype {
 
 enum iwb_mode {
     IWB_MODE_EXACT = 0, /* IEEE replay of the reference's operation order (bit-exact masks/counts) */
-    IWB_MODE_FAST = 1   /* FMA contraction + reciprocal multiplies; energies within 1e-10       */
+    IWB_MODE_FAST = 1   /* IWB_F64 only: FMA contraction + reciprocal multiplies; energies within 1e-10, */
+                        /* sign counts may differ inside the rounding-noise core (3D evaluator only)     */
 };
 
 typedef struct iwb_handle iwb_handle;

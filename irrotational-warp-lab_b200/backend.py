@@ -84,12 +84,15 @@ class _ShellClosure:
 
 def compute_energy_3d(*, rho: float, sigma: float, v: float, extent: float, n: int,
                       backend: str = BACKEND_NAME, dtype: str = "float64",
-                      shells=None, emit_rho: bool = False) -> dict:
+                      shells=None, emit_rho: bool = False, mode: str = "exact") -> dict:
     """Full 3D Cartesian volume integration, dV = dx dy dz, on the fused engine.
 
     Returns the reference's dictionary (mode, backend, dtype, grid, timing_s, energies,
     ``_e_at_r``) plus ``counts`` and ``engine`` blocks.  ``shells`` defaults to the
     reference's tail radii (8 rho, 12 rho) so that ``_e_at_r(r1)``, ``_e_at_r(r2)`` cost nothing.
+    ``mode="exact"`` (default) replays the reference's IEEE operations: bit-exact masks and sign counts.
+    ``mode="fast"`` (float64 only) contracts FMAs and multiplies by reciprocals: energies within 1e-10, sign
+    counts may differ where rho is rounding noise (inside the bubble).
     """
     eng, backend_name = resolve_backend(backend)
     x, dx = _grid(-extent, extent, n, dtype)
@@ -100,7 +103,7 @@ def compute_energy_3d(*, rho: float, sigma: float, v: float, extent: float, n: i
 
     def evaluate(radii, out=None):
         return eng.energy3d(x=x, y=y, z=z, dx=dx, dy=dy, dz=dz, rho=rho, sigma=sigma, v=v,
-                            dtype=dtype, shells=radii, eps=EPS, rho_out=out)
+                            dtype=dtype, shells=radii, eps=EPS, rho_out=out, mode=mode)
 
     t0 = time.perf_counter()
     res = evaluate(shells, rho_out)
@@ -118,7 +121,7 @@ def compute_energy_3d(*, rho: float, sigma: float, v: float, extent: float, n: i
         "energies": {"e_pos": e_pos, "e_neg": e_neg, "e_net": e_net, **summary_metrics(e_pos, e_neg)},
         "counts": {"pos": res["cnt_pos"], "neg": res["cnt_neg"], "zero": res["cnt_zero"], "nan": res["cnt_nan"],
                    "shell_points": dict(zip(shells, res["shell_cnt"]))},
-        "engine": {"name": "irrotational-warp-lab_b200", "device": eng.name, "kernel_ms": res["kernel_ms"]},
+        "engine": {"name": "irrotational-warp-lab_b200", "device": eng.name, "kernel_ms": res["kernel_ms"], "mode": mode},
         "_e_at_r": _ShellClosure(evaluate, known),
     }
     if emit_rho:

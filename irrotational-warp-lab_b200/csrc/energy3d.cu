@@ -9,65 +9,19 @@
 #include <chrono>
 #include <string>
 
-#include "energy3d.cuh"
+#include "energy3d_launch.cuh"
 #include "host_common.h"
 
 namespace iwb {
 
-// ---- kernel geometry variants -----------------------------------------------------------------
-//   config 0: region 32 x 64, 16 warps (180 KB smem)  -- built for every variant
-//   config 1: region 40 x 64, 20 warps (225 KB smem)  -- default; built for <= 2 shells without rho emission
-// One CTA per SM.  (Measured alternatives, n = 1024^3 fp64: 36x64/18 warps 72, 32x64/8 warps 52,
-// two CTAs per SM of 20x64/10 warps 64 Gpoints/s against 77 for config 1; profiles/r1_k_energy3d_history.txt.)
-struct K3Config { int rj, nw; };
-static const K3Config kConfigs[] = {{32, 16}, {40, 20}};
-constexpr int kNumConfigs = 2;
-
-template <int DT, int NSH, int RJ, int NW, bool EMIT, int MINB>
-static cudaError_t launch_one(const K3Params& P, int sm_count, cudaStream_t st)
+static cudaError_t launch_k3(int dtype, int mode, int nshell, bool emit, int cfg, const K3Params& P, int sm_count, cudaStream_t st)
 {
-    auto kern = k_energy3d<DT, NSH, RJ, NW, EMIT, MINB>;
-    constexpr size_t smem = Geo<RJ, NW>::SMEM_BYTES;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    int grid = sm_count * per_sm;
-    if (grid > P.nitems) grid = P.nitems;
-    kern<<<grid, NW * 32, smem, st>>>(P);
-    return cudaGetLastError();
-}
-
-static bool config_is_built(int cfg, int dtype, int nshell, bool emit)
-{
-    (void)dtype;
-    if (cfg == 0) return true;
-    return cfg == 1 && nshell <= 2 && !emit;
-}
-
-template <int DT, int NSH, bool EMIT>
-static cudaError_t launch_cfg(int cfg, const K3Params& P, int sm_count, cudaStream_t st)
-{
-    if (NSH == 2 && !EMIT && cfg == 1) return launch_one<DT, 2, 40, 20, false, 1>(P, sm_count, st);
-    return launch_one<DT, NSH, 32, 16, EMIT, 1>(P, sm_count, st);
-}
-
-template <int DT, bool EMIT>
-static cudaError_t launch_nsh(int nshell, int cfg, const K3Params& P, int sm_count, cudaStream_t st)
-{
-    if (nshell <= 2) return launch_cfg<DT, 2, EMIT>(cfg, P, sm_count, st);
-    return launch_cfg<DT, IWB_MAX_SHELLS, EMIT>(cfg, P, sm_count, st);
-}
-
-static cudaError_t launch_k3(int dtype, int nshell, bool emit, int cfg, const K3Params& P, int sm_count, cudaStream_t st)
-{
+    if (mode == IWB_MODE_FAST) return launch_k3_fast(nshell, emit, cfg, P, sm_count, st);
     if (dtype == IWB_F64)
-        return emit ? launch_nsh<IWB_F64, true>(nshell, cfg, P, sm_count, st)
-                    : launch_nsh<IWB_F64, false>(nshell, cfg, P, sm_count, st);
-    return emit ? launch_nsh<IWB_F32_REF, true>(nshell, cfg, P, sm_count, st)
-                : launch_nsh<IWB_F32_REF, false>(nshell, cfg, P, sm_count, st);
+        return emit ? launch_nsh<IWB_F64, true, 0>(nshell, cfg, P, sm_count, st)
+                    : launch_nsh<IWB_F64, false, 0>(nshell, cfg, P, sm_count, st);
+    return emit ? launch_nsh<IWB_F32_REF, true, 0>(nshell, cfg, P, sm_count, st)
+                : launch_nsh<IWB_F32_REF, false, 0>(nshell, cfg, P, sm_count, st);
 }
 
 static int validate(const iwb_params3d* p)
@@ -75,7 +29,9 @@ static int validate(const iwb_params3d* p)
     if (!p) return fail(IWB_ERR_INVALID, "params is NULL");
     if (p->dtype != IWB_F64 && p->dtype != IWB_F32_REF)
         return fail(IWB_ERR_INVALID, "energy3d: dtype must be IWB_F64 or IWB_F32_REF (IWB_F32_STRICT is not built yet)");
-    if (p->mode != IWB_MODE_EXACT) return fail(IWB_ERR_INVALID, "energy3d: only IWB_MODE_EXACT is built");
+    if (p->mode != IWB_MODE_EXACT && p->mode != IWB_MODE_FAST) return fail(IWB_ERR_INVALID, "energy3d: unknown mode");
+    if (p->mode == IWB_MODE_FAST && p->dtype != IWB_F64)
+        return fail(IWB_ERR_INVALID, "energy3d: IWB_MODE_FAST exists for IWB_F64 only");
     if (p->n0 < 3 || p->n1 < 3 || p->n2 < 3)
         return fail(IWB_ERR_GRID_TOO_SMALL, "Shape of array too small to calculate a numerical gradient, "
                                             "at least (edge_order + 1) elements are required.");
@@ -92,7 +48,7 @@ static int validate(const iwb_params3d* p)
 // Everything a launch needs besides the output table.
 struct Launch3 {
     K3Params P;
-    int dtype, nshell, cfg_id, ntiles, fb0, fb1;
+    int dtype, mode, nshell, cfg_id, ntiles, fb0, fb1;
     bool emit;
 };
 
@@ -176,7 +132,7 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
         IWB_CUDA(cudaMemsetAsync(counter.p, 0, 256, st));
     }
     P.counter = (unsigned int*)counter.p;
-    L->dtype = p->dtype; L->nshell = p->nshell; L->cfg_id = cfg_id; L->ntiles = ntiles; L->emit = rho_dev != nullptr;
+    L->dtype = p->dtype; L->mode = p->mode; L->nshell = p->nshell; L->cfg_id = cfg_id; L->ntiles = ntiles; L->emit = rho_dev != nullptr;
     L->fb0 = p->i_begin / FLUSH; L->fb1 = (p->i_end + FLUSH - 1) / FLUSH;
     return IWB_OK;
 }
@@ -184,7 +140,7 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
 // Fused kernel + fixed-order tile reduction into rows [fb0, fb1) of `table`; no host<->device copy.
 static int launch_slab(iwb_handle* h, const Launch3& L, double* table, cudaStream_t st)
 {
-    cudaError_t e = launch_k3(L.dtype, L.nshell, L.emit, L.cfg_id, L.P, h->sm_count, st);
+    cudaError_t e = launch_k3(L.dtype, L.mode, L.nshell, L.emit, L.cfg_id, L.P, h->sm_count, st);
     if (e != cudaSuccess) return fail(IWB_ERR_CUDA, std::string("k_energy3d launch: ") + cudaGetErrorString(e));
     k_reduce_tiles<<<L.fb1 - L.fb0, 128, 0, st>>>(L.P.partial, table, L.fb0, L.ntiles, L.P.counter);
     IWB_CUDA(cudaGetLastError());

@@ -84,7 +84,7 @@ struct Geo {
     static constexpr size_t SMEM_BYTES = (size_t(NPLANES) * PLANE + 2 * SMEM_PAD + RJ + SCRATCH) * sizeof(double);
 };
 
-template <int DT, int NSH, int RJ, int NW, bool EMIT, int MINB = 1>
+template <int DT, int NSH, int RJ, int NW, bool EMIT, int MINB = 1, int MODE = 0>
 __global__ void __launch_bounds__(NW * 32, MINB)
 k_energy3d(const __grid_constant__ K3Params P)
 {
@@ -177,7 +177,7 @@ k_energy3d(const __grid_constant__ K3Params P)
         // the pure interior formula (no branches: the two columns of a thread interleave freely);
         // EDGE = true adds the one-sided formulas at the global faces.
         auto dZ = [&](const double* B, int idx, unsigned cf, auto edge_tag) -> double {
-            double d = cdiv(B[idx + 1] - B[idx - 1], cz.h2, cz.rh2);
+            double d = cdivm<MODE>(B[idx + 1] - B[idx - 1], cz.h2, cz.rh2);
             if (decltype(edge_tag)::value) {
                 if (cf & 2u) d = edge3(cz.a0, B[idx], cz.b0, B[idx + 1], cz.c0, B[idx + 2]);
                 else if (cf & 4u) d = edge3(cz.a1, B[idx - 2], cz.b1, B[idx - 1], cz.c1, B[idx]);
@@ -190,7 +190,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                 if (jedge == 1) return edge3(cy.a0, B[idx], cy.b0, B[idx + RK], cy.c0, B[idx + 2 * RK]);
                 if (jedge == 2) return edge3(cy.a1, B[idx - 2 * RK], cy.b1, B[idx - RK], cy.c1, B[idx]);
             }
-            return cdiv(B[idx + RK] - B[idx - RK], cy.h2, cy.rh2);
+            return cdivm<MODE>(B[idx + RK] - B[idx - RK], cy.h2, cy.rh2);
         };
 
         // ---- task P(p): phi(p) at the own columns, and the x-derivative it completes -----------------
@@ -216,7 +216,8 @@ k_energy3d(const __grid_constant__ K3Params P)
                     // the row through the origin (r == 0 at one lane) takes the reference flavour
                     const bool origin_row = (p == P.i_zero) && (j0 - 2 + jr == P.j_zero);
                     // (exotic grids / parameters fail the host's operand-range proof: reference flavour throughout)
-                    phi_exact_f64<2, true>(s, xp, pc, f, origin_row || !pc.prechecked);
+                    if (MODE == 0) phi_exact_f64<2, true>(s, xp, pc, f, origin_row || !pc.prechecked);
+                    else phi_fast_f64<2>(s, xp, pc, f, origin_row || !pc.prechecked);
                 } else {
                     const float sxy = __fadd_rn((float)xxp, (float)yy_s[jr]);
                     const float s[2] = {__fadd_rn(sxy, (float)zz0), __fadd_rn(sxy, (float)zz1)};
@@ -226,8 +227,8 @@ k_energy3d(const __grid_constant__ K3Params P)
                 ph_p[base] = f[0];
                 ph_p[base + 32] = f[1];
                 if (do_px) {
-                    px_w[base] = cdiv(f[0] - ph_m2[base], cx.h2, cx.rh2);
-                    px_w[base + 32] = cdiv(f[1] - ph_m2[base + 32], cx.h2, cx.rh2);
+                    px_w[base] = cdivm<MODE>(f[0] - ph_m2[base], cx.h2, cx.rh2);
+                    px_w[base + 32] = cdivm<MODE>(f[1] - ph_m2[base + 32], cx.h2, cx.rh2);
                 }
                 if (EDGE && do_px0) {
                     px_ring[base] = edge3(cx.a0, ph_m2[base], cx.b0, ph_m1[base], cx.c0, f[0]);
@@ -353,7 +354,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                     else if (EDGE && iedge == 2)   // phi_x(n0-3), (n0-2), (n0-1)
                         pxx = edge3(cx.a1, px_m2[idx], cx.b1, px_m[idx], cx.c1, px_i[idx]);
                     else
-                        pxx = cdiv(px_p[idx] - px_m[idx], cx.h2, cx.rh2);
+                        pxx = cdivm<MODE>(px_p[idx] - px_m[idx], cx.h2, cx.rh2);
                     const double pxy = dY(px_i, idx, jedge, edge_tag);
                     const double pxz = dZ(px_i, idx, cf, edge_tag);
                     const double pyy = dY(py_r, idx, jedge, edge_tag);
@@ -364,7 +365,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                     const double diag = (pxx * pxx + pyy * pyy) + pzz * pzz;
                     const double off = (pxy * pxy + pxz * pxz) + pyz * pyz;
                     const double kk = fma(2.0, off, diag);     // 2.0*off is exact -> same rounding as diag + 2.0*off
-                    rho2[a] = cdiv(tr * tr - kk, P.c16pi, P.rc16pi);
+                    rho2[a] = cdivm<MODE>(tr * tr - kk, P.c16pi, P.rc16pi);
                 }
                 if (EMIT) {
                     const long long j = j0 - 2 + jr, k = k0 - 2 + tx;

@@ -50,7 +50,7 @@ class Engine:
     # -- 3D ---------------------------------------------------------------------------------
     @staticmethod
     def make_params3d(*, x, y, z, dx, dy, dz, rho, sigma, v, dtype, shells=(), eps=1e-12,
-                      i_begin=0, i_end=None, rho_out=None, rho_out_is_device=False):
+                      i_begin=0, i_end=None, rho_out=None, rho_out_is_device=False, mode="exact"):
         """Fill an ``iwb_params3d``.  ``x, y, z`` are the host linspace arrays (float32 grids are
         widened to float64 without change of value).  Returns (params, keepalive)."""
         xd, yd, zd = _as_f64(x), _as_f64(y), _as_f64(z)
@@ -59,7 +59,9 @@ class Engine:
             raise ValueError(f"at most {_capi.MAX_SHELLS} shell radii per call")
         p = _capi.Params3D()
         p.dtype = _capi.F32_REF if dtype == "float32" else _capi.F64
-        p.mode = _capi.MODE_EXACT
+        if mode not in ("exact", "fast"):
+            raise ValueError(f"Unknown mode: {mode!r} (expected: exact|fast)")
+        p.mode = _capi.MODE_FAST if mode == "fast" else _capi.MODE_EXACT
         p.n0, p.n1, p.n2 = len(xd), len(yd), len(zd)
         p.i_begin = int(i_begin)
         p.i_end = len(xd) if i_end is None else int(i_end)
