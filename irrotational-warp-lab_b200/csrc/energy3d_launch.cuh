@@ -6,8 +6,8 @@
 namespace iwb {
 
 // ---- kernel geometry variants -----------------------------------------------------------------
-//   config 0: region 32 x 64, 16 warps (180 KB smem)  -- built for every variant
-//   config 1: region 40 x 64, 20 warps (225 KB smem)  -- default; built for <= 2 shells without rho emission
+//   config 0: region 32 x 64, 16 warps (180 KB smem)
+//   config 1: region 40 x 64, 20 warps (225 KB smem)  -- default
 // One CTA per SM.  (Measured alternatives, n = 1024^3 fp64: 36x64/18 warps 72, 32x64/8 warps 52,
 // two CTAs per SM of 20x64/10 warps 64 Gpoints/s against 77 for config 1; profiles/r1_k_energy3d_history.txt.)
 struct K3Config { int rj, nw; };
@@ -33,15 +33,15 @@ static cudaError_t launch_one(const K3Params& P, int sm_count, cudaStream_t st)
 
 static bool config_is_built(int cfg, int dtype, int nshell, bool emit)
 {
-    (void)dtype;
-    if (cfg == 0) return true;
-    return cfg == 1 && nshell <= 2 && !emit;
+    (void)dtype; (void)nshell; (void)emit;
+    return cfg == 0 || cfg == 1;       // every variant exists in both geometries: the tiling (and with it the
+                                       // summation order) must not depend on emit_rho or on the number of shells
 }
 
 template <int DT, int NSH, bool EMIT, int MODE>
 static cudaError_t launch_cfg(int cfg, const K3Params& P, int sm_count, cudaStream_t st)
 {
-    if (NSH == 2 && !EMIT && cfg == 1) return launch_one<DT, 2, 40, 20, false, 1, MODE>(P, sm_count, st);
+    if (cfg == 1) return launch_one<DT, NSH, 40, 20, EMIT, 1, MODE>(P, sm_count, st);
     return launch_one<DT, NSH, 32, 16, EMIT, 1, MODE>(P, sm_count, st);
 }
 
