@@ -5,14 +5,26 @@
   * :func:`objective_neg_energy_3d` -- BASELINE config 5's extension: |E-| of the 3D exact-potential volume
   * :func:`evaluate_objective_3d_batch` -- the ``n_initial_points`` / grid batches of config 5 as one engine call
 
+  * :func:`optimize_nelder_mead`    <- ``optimize_nelder_mead`` (:134-209)  SciPy simplex, penalty bounds
+  * :func:`optimize_hybrid`         <- ``optimize_hybrid``      (:212-272)  grid search, then simplex
+  * :func:`optimize_bayesian`       <- ``optimize_bayesian``    (:275-356)  scikit-optimize ``gp_minimize``
+
 The optimisers themselves (SciPy Nelder-Mead, scikit-optimize ``gp_minimize``) stay on the host with
-their sequential ask/tell order; they take these objectives as plain callables.
+their sequential ask/tell order; only the objective runs on the engine.  Every driver takes
+``objective="slice2d"`` (the reference's semantics) or ``objective="volume3d"`` (BASELINE config 5).
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
 
 import numpy as np
+
+try:                                     # optional, exactly as in the reference (optimize.py:9-14)
+    from skopt import gp_minimize
+    from skopt.space import Real
+    SKOPT_AVAILABLE = True
+except ImportError:
+    SKOPT_AVAILABLE = False
 
 from .backend import EPS, _grid
 from .engine import get_engine
@@ -75,3 +87,92 @@ def objective_neg_energy_3d(params, param_names, rho: float, extent: float, n: i
     """Drop-in objective with the 3D evaluator (same signature as :func:`objective_neg_energy`)."""
     d = dict(zip(param_names, params))
     return evaluate_objective_3d_batch([(d.get("sigma", 3.0), d.get("v", 1.5))], rho, extent, n, dtype)[0]
+
+
+def _objective(kind: str):
+    if kind == "slice2d":
+        return objective_neg_energy
+    if kind == "volume3d":
+        return objective_neg_energy_3d
+    raise ValueError(f"Unknown objective: {kind!r} (expected: slice2d|volume3d)")
+
+
+def optimize_nelder_mead(*, rho: float, initial_sigma: float, initial_v: float, extent: float, n: int,
+                         bounds: dict | None = None, objective: str = "slice2d") -> OptimizationResult:
+    """Local simplex search from (initial_sigma, initial_v); points outside ``bounds`` cost 1e10 per violated bound
+    (Nelder-Mead has no native bounds).  maxiter 100, xatol 1e-4, fatol 1e-6 as in the reference."""
+    from scipy.optimize import minimize
+
+    names = ["sigma", "v"]
+    fun = _objective(objective)
+    s_lo, s_hi = (bounds or {}).get("sigma", (0.1, 100.0))
+    v_lo, v_hi = (bounds or {}).get("v", (0.01, 10.0))
+
+    def cost(params):
+        if bounds is not None:
+            sigma, v = params
+            penalty = (1e10 if (sigma < s_lo or sigma > s_hi) else 0.0) + (1e10 if (v < v_lo or v > v_hi) else 0.0)
+            if penalty > 0:
+                return penalty
+        return fun(params, names, rho, extent, n)
+
+    n_evals = [0]
+
+    def counted(params):
+        n_evals[0] += 1
+        return cost(params)
+
+    x0 = np.array([initial_sigma, initial_v])
+    initial_value = cost(x0)
+    res = minimize(counted, x0, method="Nelder-Mead", options={"maxiter": 100, "xatol": 1e-4, "fatol": 1e-6})
+    return OptimizationResult(best_params={"sigma": res.x[0], "v": res.x[1]}, best_value=res.fun,
+                              initial_params={"sigma": initial_sigma, "v": initial_v}, initial_value=initial_value,
+                              n_evaluations=n_evals[0], success=res.success, method="nelder_mead", message=res.message)
+
+
+def optimize_hybrid(*, rho: float, sigma_range, v_range, sigma_steps: int, v_steps: int, extent: float, n: int,
+                    refine: bool = True, objective: str = "slice2d") -> OptimizationResult:
+    """Exhaustive grid, then Nelder-Mead from the best grid point inside the same bounds."""
+    if objective == "slice2d":
+        grid = grid_search(rho=rho, sigma_range=sigma_range, v_range=v_range, sigma_steps=sigma_steps, v_steps=v_steps,
+                           extent=extent, n=n)
+    else:       # the whole grid of the 3D objective is one batched engine call
+        sig = np.linspace(sigma_range[0], sigma_range[1], sigma_steps)
+        vel = np.linspace(v_range[0], v_range[1], v_steps)
+        pts = [(s, v) for s in sig for v in vel]
+        vals = evaluate_objective_3d_batch(pts, rho, extent, n)
+        k = int(np.argmin(vals))          # first minimum, like the reference's strict "<" scan
+        grid = OptimizationResult(best_params={"sigma": pts[k][0], "v": pts[k][1]}, best_value=vals[k],
+                                  initial_params={"sigma": sig[0], "v": vel[0]}, initial_value=vals[0],
+                                  n_evaluations=len(pts), success=True, method="grid_search",
+                                  message=f"Evaluated {len(pts)} grid points")
+    if not refine:
+        return grid
+    fine = optimize_nelder_mead(rho=rho, initial_sigma=grid.best_params["sigma"], initial_v=grid.best_params["v"],
+                                extent=extent, n=n, bounds={"sigma": sigma_range, "v": v_range}, objective=objective)
+    return OptimizationResult(best_params=fine.best_params, best_value=fine.best_value, initial_params=grid.initial_params,
+                              initial_value=grid.initial_value, n_evaluations=grid.n_evaluations + fine.n_evaluations,
+                              success=fine.success, method="hybrid_grid_nelder_mead",
+                              message=f"Grid: {grid.n_evaluations} evals, Refinement: {fine.n_evaluations} evals")
+
+
+def optimize_bayesian(*, rho: float, sigma_range, v_range, extent: float, n: int, n_calls: int = 50,
+                      n_initial_points: int = 10, random_state=None, objective: str = "slice2d") -> OptimizationResult:
+    """Gaussian-process search (EI acquisition, noise 1e-10) through scikit-optimize; ImportError without it."""
+    if not SKOPT_AVAILABLE:
+        raise ImportError("Bayesian optimization requires scikit-optimize. Install with: pip install scikit-optimize")
+    fun = _objective(objective)
+    n_evals = [0]
+
+    def cost(params):
+        n_evals[0] += 1
+        return fun(np.array(params), ["sigma", "v"], rho, extent, n)
+
+    res = gp_minimize(cost, [Real(sigma_range[0], sigma_range[1], name="sigma"), Real(v_range[0], v_range[1], name="v")],
+                      n_calls=n_calls, n_initial_points=n_initial_points, random_state=random_state, acq_func="EI",
+                      noise=1e-10, verbose=False)
+    return OptimizationResult(best_params={"sigma": res.x[0], "v": res.x[1]}, best_value=res.fun,
+                              initial_params={"sigma": res.x_iters[0][0], "v": res.x_iters[0][1]},
+                              initial_value=float(res.func_vals[0]), n_evaluations=n_evals[0], success=True,
+                              method="bayesian_gp",
+                              message=f"Bayesian optimization with {n_calls} calls ({n_initial_points} initial random)")
