@@ -277,7 +277,10 @@ def main(argv=None):
         except OSError:
             pass
         hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
-        alg_bytes = 8.0 * (2 * n + n + n) + 8.0 * ROW_WIDTH * (r1 - r0)          # coordinates in, table rows out
+        # coordinates in; per-(flush block, tile) partial rows out (36 x 60 tiles of the default 40 x 64 geometry);
+        # they are consumed by k_reduce_tiles and usually never leave L2
+        ntiles = -(-n // 36) * -(-n // 60)
+        alg_bytes = 8.0 * (2 * n + n + n) + 8.0 * ROW_WIDTH * (r1 - r0) * ntiles
         line = {
             "metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
