@@ -16,6 +16,7 @@
  *   iwb_slice_z0         <- compute_slice_z0       src/irrotational_warp/adm.py:27-88
  *                           + central_diff_2d      src/irrotational_warp/fd.py:6-25
  *                           + integrate_signed     src/irrotational_warp/adm.py:91-97
+ *   iwb_radial_profile3d <- compute_radial_average_z0  src/irrotational_warp/tail.py:46-80 (its 3D generalisation)
  *   iwb_energy3d_batch   <- the serial loops of sweep_velocity
  *                           scripts/sweep_superluminal.py:59-106 and grid_search
  *                           src/irrotational_warp/optimize.py:100-114
@@ -138,6 +139,20 @@ int iwb_reduce_table(iwb_handle *h, const double *table_device, int nrows, int n
 
 /* Independent parameter points on one device; one host synchronisation at the end. */
 int iwb_energy3d_batch(iwb_handle *h, int npoints, const iwb_params3d *pts, iwb_result *outs);
+
+/* Radial-shell profile of rho_adm on the 3D grid: sum and point count over edges[k] <= r < edges[k+1], the binning
+ * rule of compute_radial_average_z0 (src/irrotational_warp/tail.py:46-80) applied to the field of compute_energy_3d
+ * (SURVEY.md §8 f3).  The field is emitted and re-read in passes of <= 1 GiB on the device and never reaches the host.
+ * `out` (may be NULL) receives the energies / counts of the same evaluation.  Deterministic and independent of the
+ * pass size; sums over [i_begin, i_end) only, so slabs can be added on the host. */
+typedef struct {
+    int32_t n_bins;            /* 1 .. 256 */
+    const double *edges;       /* host [n_bins + 1], strictly increasing (np.linspace(0, r_max, n_bins + 1)) */
+    double *sum;               /* host out [n_bins] */
+    int64_t *count;            /* host out [n_bins] */
+} iwb_profile3d;
+
+int iwb_radial_profile3d(iwb_handle *h, const iwb_params3d *p, const iwb_profile3d *prof, iwb_result *out);
 
 /* Axisymmetric half-plane, arrays [ny, nx] (x fastest), z = 0. */
 typedef struct {

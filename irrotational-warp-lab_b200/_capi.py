@@ -81,6 +81,11 @@ class SliceResultC(C.Structure):
 
 
 # every symbol include/iwb200.h declares: name -> (restype, argtypes)
+class Profile3D(C.Structure):
+    _fields_ = [("n_bins", C.c_int32), ("edges", C.POINTER(C.c_double)), ("sum", C.POINTER(C.c_double)),
+                ("count", C.POINTER(C.c_int64))]
+
+
 SYMBOLS = {
     "iwb_version": (C.c_int, []),
     "iwb_device_count": (C.c_int, []),
@@ -95,6 +100,7 @@ SYMBOLS = {
     "iwb_plan3d_run_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "iwb_plan3d_destroy": (C.c_int, [C.c_void_p]),
     "iwb_reduce_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(Result)]),
+    "iwb_radial_profile3d": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.POINTER(Profile3D), C.POINTER(Result)]),
     "iwb_energy3d_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Params3D), C.POINTER(Result)]),
     "iwb_energy_axisym": (C.c_int, [C.c_void_p, C.POINTER(ParamsAxisym), C.POINTER(Result)]),
     "iwb_slice_z0": (C.c_int, [C.c_void_p, C.POINTER(ParamsSlice), C.POINTER(SliceResultC)]),

@@ -240,7 +240,7 @@ int iwb_destroy(iwb_handle* h)
         Scratch& c = h->scr[s];
         if (c.stream) cudaStreamSynchronize(c.stream);
         c.coords.release(); c.partial.release(); c.table.release(); c.out.release(); c.rho.release(); c.counter.release();
-        c.h_coords.release(); c.h_out.release();
+        c.h_coords.release(); c.h_out.release(); c.prof.release(); c.h_prof.release();
         if (c.ev0) cudaEventDestroy(c.ev0);
         if (c.ev1) cudaEventDestroy(c.ev1);
         if (c.stream) cudaStreamDestroy(c.stream);

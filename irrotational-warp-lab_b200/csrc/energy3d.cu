@@ -10,6 +10,7 @@
 #include <string>
 
 #include "energy3d_launch.cuh"
+#include "radial_profile.cuh"
 #include "host_common.h"
 
 namespace iwb {
@@ -226,6 +227,7 @@ int iwb_energy3d(iwb_handle* h, const iwb_params3d* p, iwb_result* out)
     memset(out, 0, sizeof(*out));
     unpack_row((const double*)c.h_out.p, p->nshell, out);
     out->cnt_nan = (int64_t)(p->i_end - p->i_begin) * p->n1 * p->n2 - out->cnt_pos - out->cnt_neg - out->cnt_zero;
+    apply_reference_nonfinite(out, p->nshell);
     float ms = 0;
     IWB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
     out->kernel_ms = ms;
@@ -262,6 +264,91 @@ int iwb_reduce_table(iwb_handle* h, const double* table_device, int nrows, int n
     IWB_CUDA(cudaStreamSynchronize(st));
     memset(out, 0, sizeof(*out));
     unpack_row((const double*)c.h_out.p, nshell, out);
+    return IWB_OK;
+}
+
+int iwb_radial_profile3d(iwb_handle* h, const iwb_params3d* p, const iwb_profile3d* prof, iwb_result* out)
+{
+    if (!h || !prof) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: null argument");
+    int rc = validate(p);
+    if (rc) return rc;
+    if (p->rho_out) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: rho_out must be NULL (the field is staged internally)");
+    const int nb = prof->n_bins;
+    if (nb < 1 || nb > PROF_MAX_BINS) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: n_bins must be in [1, 256]");
+    if (!prof->edges || !prof->sum || !prof->count) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: edges / sum / count are NULL");
+    for (int q = 0; q < nb; ++q)
+        if (!(prof->edges[q + 1] > prof->edges[q])) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: edges must be strictly increasing");
+    auto t0 = std::chrono::steady_clock::now();
+    IWB_CUDA(cudaSetDevice(h->device));
+    Scratch& c = h->scr[0];
+    cudaStream_t st = c.stream;
+
+    // planes per pass: the emitted field of one pass stays <= 1 GiB (at least one flush block)
+    const size_t plane_bytes = (size_t)p->n1 * p->n2 * sizeof(double);
+    int pass = (int)(((size_t)1 << 30) / plane_bytes) / FLUSH * FLUSH;
+    if (pass < FLUSH) pass = FLUSH;
+    const int planes = p->i_end - p->i_begin;
+    if (pass > planes) pass = (planes + FLUSH - 1) / FLUSH * FLUSH;
+    const int nfb_total = (p->n0 + FLUSH - 1) / FLUSH;
+    const int fb0 = p->i_begin / FLUSH, fb1 = (p->i_end + FLUSH - 1) / FLUSH;
+
+    // device: edges[nb+1] | part_sum[nfb][SUB][nb] | part_cnt[...] | sum[nb] | cnt[nb]
+    const size_t npart = (size_t)nfb_total * PROF_SUB * nb;
+    const size_t off_psum = (size_t)nb + 1, off_pcnt = off_psum + npart, off_sum = off_pcnt + npart, off_cnt = off_sum + nb;
+    IWB_CUDA(c.prof.reserve((off_cnt + nb) * sizeof(double)));
+    IWB_CUDA(c.h_prof.reserve(((size_t)3 * nb + 1) * sizeof(double)));
+    IWB_CUDA(c.rho.reserve((size_t)pass * plane_bytes));
+    IWB_CUDA(c.table.reserve((size_t)nfb_total * ROW * sizeof(double)));
+    IWB_CUDA(c.out.reserve(ROW_BYTES_MIN));
+    IWB_CUDA(c.h_out.reserve(ROW_BYTES_MIN));
+    double* dprof = (double*)c.prof.p;
+    double* hprof = (double*)c.h_prof.p;
+    memcpy(hprof, prof->edges, ((size_t)nb + 1) * sizeof(double));
+    IWB_CUDA(cudaMemcpyAsync(dprof, hprof, ((size_t)nb + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+
+    IWB_CUDA(cudaEventRecord(c.ev0, st));
+    for (int ia = p->i_begin; ia < p->i_end; ia += pass) {
+        iwb_params3d q = *p;
+        q.i_begin = ia;
+        q.i_end = (ia + pass < p->i_end) ? ia + pass : p->i_end;
+        IWB_CUDA(cudaStreamSynchronize(st));       // the coordinate staging buffer and the rho pass buffer are reused
+        Launch3 L;
+        rc = prepare_slab(h, &q, c.h_coords, c.coords, c.partial, c.counter, st, (double*)c.rho.p, &L);
+        if (rc) return rc;
+        rc = launch_slab(h, L, (double*)c.table.p, st);
+        if (rc) return rc;
+        ProfParams R;
+        R.rho = (const double*)c.rho.p;
+        R.xx = L.P.xx; R.yy = L.P.yy; R.zz = L.P.zz;
+        R.edges = dprof;
+        R.n1 = p->n1; R.n2 = p->n2; R.i_begin = q.i_begin; R.i_end = q.i_end; R.nb = nb; R.dtype = p->dtype;
+        R.inv_width = (double)nb / prof->edges[nb];
+        R.part_sum = dprof + off_psum;
+        R.part_cnt = (long long*)(dprof + off_pcnt);
+        k_radial_hist<<<dim3(PROF_SUB, L.fb1 - L.fb0), PROF_NW * 32, 0, st>>>(R);
+        IWB_CUDA(cudaGetLastError());
+    }
+    k_radial_reduce<<<(nb + 63) / 64, 64, 0, st>>>(dprof + off_psum, (const long long*)(dprof + off_pcnt), fb0, fb1, nb,
+                                                   dprof + off_sum, (long long*)(dprof + off_cnt));
+    IWB_CUDA(cudaGetLastError());
+    k_reduce_rows<<<1, 128, 0, st>>>((const double*)c.table.p + (size_t)fb0 * ROW, (double*)c.out.p, fb1 - fb0);
+    IWB_CUDA(cudaGetLastError());
+    IWB_CUDA(cudaEventRecord(c.ev1, st));
+    IWB_CUDA(cudaMemcpyAsync(hprof, dprof + off_sum, (size_t)2 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+    IWB_CUDA(cudaMemcpyAsync(c.h_out.p, c.out.p, ROW_BYTES_MIN, cudaMemcpyDeviceToHost, st));
+    IWB_CUDA(cudaStreamSynchronize(st));
+    memcpy(prof->sum, hprof, (size_t)nb * sizeof(double));
+    memcpy(prof->count, hprof + nb, (size_t)nb * sizeof(int64_t));
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        unpack_row((const double*)c.h_out.p, p->nshell, out);
+        out->cnt_nan = (int64_t)planes * p->n1 * p->n2 - out->cnt_pos - out->cnt_neg - out->cnt_zero;
+        apply_reference_nonfinite(out, p->nshell);
+        float ms = 0;
+        IWB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+        out->kernel_ms = ms;
+        out->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
     return IWB_OK;
 }
 
@@ -329,6 +416,7 @@ int iwb_energy3d_batch(iwb_handle* h, int npoints, const iwb_params3d* pts, iwb_
             unpack_row((const double*)c.h_out.p, pts[base + q].nshell, &outs[base + q]);
             outs[base + q].cnt_nan = (int64_t)(pts[base + q].i_end - pts[base + q].i_begin) * pts[base + q].n1 * pts[base + q].n2 -
                                      outs[base + q].cnt_pos - outs[base + q].cnt_neg - outs[base + q].cnt_zero;
+            apply_reference_nonfinite(&outs[base + q], pts[base + q].nshell);
             float ms = 0;
             IWB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
             outs[base + q].kernel_ms = ms;

@@ -59,10 +59,30 @@ struct Scratch {
     DevBuf out;        // [ROW]
     DevBuf rho;        // staging for a host rho_out
     DevBuf counter;    // dynamic work-item counter of k_energy3d
+    DevBuf prof;       // radial profile: edges | per-(flush block, CTA) partials | result
+    PinBuf h_prof;
     PinBuf h_coords;
     PinBuf h_out;      // [ROW]
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
+
+// The reference multiplies by the masks (e * (e > 0), reproduce_rodal_exact.py:57-61, 220-224), so a non-finite
+// point poisons sums it does not belong to: NaN * 0 and inf * 0 are NaN.  The kernels select instead of multiplying
+// (no extra work per point); this restores the reference's result for a field with non-finite points.  A shell sum
+// that is itself infinite keeps its value (the infinite point lies inside that shell).
+inline void apply_reference_nonfinite(iwb_result* r, int nshell)
+{
+    const double qnan = __builtin_nan("");
+    const bool any_nan = r->cnt_nan > 0;
+    const bool pinf = __builtin_isinf(r->e_pos), ninf = __builtin_isinf(r->e_neg);
+    if (!any_nan && !pinf && !ninf) return;
+    if (any_nan || ninf) r->e_pos = qnan;
+    if (any_nan || pinf) r->e_neg = qnan;
+    for (int s = 0; s < nshell; ++s) {
+        if (any_nan || ninf || (pinf && !__builtin_isinf(r->shell_pos[s]))) r->shell_pos[s] = qnan;
+        if (any_nan || pinf || (ninf && !__builtin_isinf(r->shell_neg[s]))) r->shell_neg[s] = qnan;
+    }
+}
 
 constexpr int NSCRATCH = 4;
 constexpr size_t ROW_BYTES_MIN = IWB_ROW_WIDTH * sizeof(double);

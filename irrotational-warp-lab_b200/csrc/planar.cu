@@ -397,6 +397,7 @@ int iwb_energy_axisym(iwb_handle* h, const iwb_params_axisym* p, iwb_result* out
     IWB_CUDA(cudaStreamSynchronize(c.stream));
     memset(out, 0, sizeof(*out));
     unpack_row((const double*)c.h_out.p, p->nshell, out);
+    apply_reference_nonfinite(out, p->nshell);
     float ms = 0;
     IWB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
     out->kernel_ms = ms;

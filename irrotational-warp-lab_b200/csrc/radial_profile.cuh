@@ -1,0 +1,100 @@
+// Radial-shell profile of rho_adm on the 3D grid: per-bin sum and point count over the spherical shells
+// edges[k] <= r < edges[k+1].  This is the binning rule of compute_radial_average_z0
+// (/root/reference/src/irrotational_warp/tail.py:46-80: equal-width bins from 0 to max r, half-open, so the farthest
+// point belongs to no bin) applied to the 3D field of compute_energy_3d instead of the z = 0 slice.
+//
+// The fused kernel emits rho for a slab of planes (8 B/point, the only time the field reaches HBM); k_radial_hist reads
+// it back once.  Deterministic by construction: a flush block of IWB_FLUSH_PLANES planes is split over PROF_SUB CTAs
+// and PROF_NW warps by row index; every warp owns a private histogram that only its lane 0 updates, one bin at a time
+// (the lanes of one bin are added by a fixed shuffle tree); warps, CTAs and flush blocks are then added in index
+// order.  The result therefore depends neither on scheduling nor on how the planes were cut into passes or slabs.
+#pragma once
+#include "energy3d.cuh"
+
+namespace iwb {
+
+constexpr int PROF_MAX_BINS = 256;
+constexpr int PROF_SUB = 8;       // CTAs per flush block
+constexpr int PROF_NW = 8;        // warps per CTA
+
+struct ProfParams {
+    const double* rho;            // [i_end - i_begin][n1][n2]
+    const double *xx, *yy, *zz;   // squared coordinates as staged for k_energy3d
+    const double* edges;          // [nb + 1]
+    int n1, n2, i_begin, i_end, nb, dtype;
+    double inv_width;             // nb / edges[nb]: first guess of the bin, corrected against the edges
+    double* part_sum;             // [flush block][PROF_SUB][nb]
+    long long* part_cnt;
+};
+
+static __global__ void __launch_bounds__(PROF_NW * 32) k_radial_hist(const ProfParams P)
+{
+    __shared__ double s_edges[PROF_MAX_BINS + 1];
+    __shared__ double s_sum[PROF_NW][PROF_MAX_BINS];
+    __shared__ int s_cnt[PROF_NW][PROF_MAX_BINS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = P.nb;
+    for (int q = threadIdx.x; q <= nb; q += blockDim.x) s_edges[q] = P.edges[q];
+    for (int q = lane; q < nb; q += 32) { s_sum[warp][q] = 0.0; s_cnt[warp][q] = 0; }
+    __syncthreads();
+
+    const int sub = blockIdx.x;
+    const int fb = P.i_begin / FLUSH + blockIdx.y;
+    const int ia = fb * FLUSH, ib = min(ia + FLUSH, P.i_end);
+    const int nrows = (ib - ia) * P.n1;
+    for (int row = sub * PROF_NW + warp; row < nrows; row += PROF_SUB * PROF_NW) {
+        const int i = ia + row / P.n1, j = row - (row / P.n1) * P.n1;
+        const double* src = P.rho + ((size_t)(i - P.i_begin) * P.n1 + j) * P.n2;
+        const double sxy = P.xx[i] + P.yy[j];
+        const float sxy_f = __fadd_rn((float)P.xx[i], (float)P.yy[j]);
+        for (int k0 = 0; k0 < P.n2; k0 += 32) {
+            const int k = k0 + lane;
+            const bool valid = k < P.n2;
+            double v = 0.0, r = 0.0;
+            if (valid) {
+                v = src[k];
+                // the same r as the evaluator's (reproduce_rodal_exact.py:179, 218)
+                r = (P.dtype == IWB_F64) ? sqrt(sxy + P.zz[k]) : (double)__fsqrt_rn(__fadd_rn(sxy_f, (float)P.zz[k]));
+            }
+            int kb = min((int)(r * P.inv_width), nb - 1);
+            while (kb > 0 && r < s_edges[kb]) --kb;
+            while (kb < nb && r >= s_edges[kb + 1]) ++kb;     // kb == nb: on or beyond the last edge, in no bin
+            const bool in_bin = valid && kb < nb;
+            unsigned todo = __ballot_sync(0xffffffffu, in_bin);
+            while (todo) {
+                const int b = __shfl_sync(0xffffffffu, kb, __ffs(todo) - 1);
+                const bool mine = in_bin && kb == b;
+                const unsigned same = __ballot_sync(0xffffffffu, mine);
+                double t = mine ? v : 0.0;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+                if (lane == 0) { s_sum[warp][b] += t; s_cnt[warp][b] += __popc(same); }
+                todo &= ~same;
+            }
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < nb; q += blockDim.x) {
+        double a = s_sum[0][q];
+        long long c = s_cnt[0][q];
+        for (int w = 1; w < PROF_NW; ++w) { a += s_sum[w][q]; c += s_cnt[w][q]; }
+        const size_t o = ((size_t)fb * PROF_SUB + sub) * nb + q;
+        P.part_sum[o] = a;
+        P.part_cnt[o] = c;
+    }
+}
+
+// flush blocks [fb0, fb1) x PROF_SUB partials -> [nb], in index order
+static __global__ void k_radial_reduce(const double* __restrict__ part_sum, const long long* __restrict__ part_cnt,
+                                       int fb0, int fb1, int nb, double* __restrict__ sum, long long* __restrict__ cnt)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nb) return;
+    double a = 0.0;
+    long long c = 0;
+    for (size_t s = (size_t)fb0 * PROF_SUB; s < (size_t)fb1 * PROF_SUB; ++s) { a += part_sum[s * nb + q]; c += part_cnt[s * nb + q]; }
+    sum[q] = a;
+    cnt[q] = c;
+}
+
+}  // namespace iwb

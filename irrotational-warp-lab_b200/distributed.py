@@ -42,6 +42,7 @@ def compute_energy_3d_sharded(*, rho, sigma, v, extent, n, dtype="float64", shel
         full = sharding.all_gather_table(table[r0:r1], n, world, group=group)
         res = eng.reduce_table(full.data_ptr(), full.shape[0], len(radii), stream.cuda_stream)
         res["cnt_nan"] = n ** 3 - res["cnt_pos"] - res["cnt_neg"] - res["cnt_zero"]
+        sharding.apply_reference_nonfinite(res)
         del keep
         return res
 

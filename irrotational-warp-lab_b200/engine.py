@@ -102,6 +102,26 @@ class Engine:
         del keep
         return self._result_dict(r, p.nshell)
 
+    def radial_profile3d(self, edges, **kw):
+        """Per-bin sum and count of rho_adm over ``edges[k] <= r < edges[k+1]`` plus the energies of the same
+        evaluation (iwb_radial_profile3d)."""
+        edges = np.ascontiguousarray(edges, dtype=np.float64)
+        nb = len(edges) - 1
+        p, keep = self.make_params3d(**kw)
+        sums = np.zeros(max(nb, 1), dtype=np.float64)
+        counts = np.zeros(max(nb, 1), dtype=np.int64)
+        prof = _capi.Profile3D()
+        prof.n_bins = nb
+        prof.edges = edges.ctypes.data_as(C.POINTER(C.c_double))
+        prof.sum = sums.ctypes.data_as(C.POINTER(C.c_double))
+        prof.count = counts.ctypes.data_as(C.POINTER(C.c_int64))
+        r = _capi.Result()
+        _capi.check(self._lib.iwb_radial_profile3d(self._h, C.byref(p), C.byref(prof), C.byref(r)))
+        del keep
+        out = self._result_dict(r, p.nshell)
+        out["bin_sum"], out["bin_count"] = sums[:nb], counts[:nb]
+        return out
+
     def energy3d_batch(self, points):
         """``points``: list of kwargs for :meth:`make_params3d`; one host sync for the whole batch."""
         n = len(points)

@@ -16,6 +16,8 @@ Pure host logic; imports neither CUDA nor the oracle, and is exercised on CPU wi
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 from ._capi import FLUSH_PLANES, MAX_SHELLS, ROW_WIDTH
@@ -67,7 +69,29 @@ def reduce_table_host(table: np.ndarray, nshell: int, n_points: int | None = Non
     }
     if n_points is not None:
         out["cnt_nan"] = int(n_points) - out["cnt_pos"] - out["cnt_neg"] - out["cnt_zero"]
+        apply_reference_nonfinite(out)
     return out
+
+
+def apply_reference_nonfinite(res: dict) -> dict:
+    """Host twin of ``apply_reference_nonfinite`` (csrc/host_common.h): the reference multiplies by its masks
+    (``e * (e > 0)``, reproduce_rodal_exact.py:57-61, 220-224), so NaN * 0 and inf * 0 poison every sum; the
+    kernels select instead, and this puts the reference's NaNs back.  In place; needs ``cnt_nan``."""
+    nan = float("nan")
+    any_nan = res["cnt_nan"] > 0
+    pinf, ninf = math.isinf(res["e_pos"]), math.isinf(res["e_neg"])
+    if not (any_nan or pinf or ninf):
+        return res
+    if any_nan or ninf:
+        res["e_pos"] = nan
+    if any_nan or pinf:
+        res["e_neg"] = nan
+    for s in range(len(res["shell_pos"])):
+        if any_nan or ninf or (pinf and not math.isinf(res["shell_pos"][s])):
+            res["shell_pos"][s] = nan
+        if any_nan or pinf or (ninf and not math.isinf(res["shell_neg"][s])):
+            res["shell_neg"][s] = nan
+    return res
 
 
 def pack_row(e_pos, e_neg, cnt_pos, cnt_neg, cnt_zero, shell_pos=(), shell_neg=(), shell_cnt=()) -> np.ndarray:

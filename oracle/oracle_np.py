@@ -316,3 +316,37 @@ def integrate_signed(field, dx, dy):
 # --------------------------------------------------------------------------- #
 def two_point_tail(e_r1, e_r2, r1, r2):
     return float(e_r2 + (r1 / (r2 - r1)) * (e_r2 - e_r1))
+
+
+def radial_profile_3d(*, rho, sigma, v, extent, n, n_bins=50, dtype="float64", i_begin=0, i_end=None):
+    """Radial-shell profile of the 3D rho_adm: the binning of compute_radial_average_z0
+    (/root/reference/src/irrotational_warp/tail.py:59-78 -- ``edges = linspace(0, max(R), n_bins + 1)``, masks
+    ``(R >= edges[k]) & (R < edges[k+1])``, ``np.mean`` of the selected points, 0 for an empty bin) applied to the
+    field of :func:`energy_3d`.  The edges always come from the FULL grid; ``i_begin``/``i_end``
+    restrict which planes are binned.  Also returns per-bin sum, count and sum of |rho| (the scale for tolerances)."""
+    i_end = n if i_end is None else i_end
+    full = energy_3d(rho=rho, sigma=sigma, v=v, extent=extent, n=n, dtype=dtype, i_begin=i_begin, i_end=i_end,
+                     return_density=True)
+    field = full["e_density"] / full["dV"]
+    x, _ = grid_axis(-extent, extent, n, dtype)
+    X, Y, Z = np.meshgrid(x[i_begin:i_end], x, x, indexing="ij")
+    R = np.sqrt(X * X + Y * Y + Z * Z)
+    xm = np.max(x * x)
+    r_max = np.sqrt((xm + xm) + xm)
+    if i_begin == 0 and i_end == n:
+        assert r_max == np.max(R)
+    edges = np.linspace(0, r_max, n_bins + 1)
+    centres = 0.5 * (edges[:-1] + edges[1:])
+    avg = np.zeros(n_bins)
+    tot = np.zeros(n_bins)
+    tot_abs = np.zeros(n_bins)
+    cnt = np.zeros(n_bins, dtype=np.int64)
+    for k in range(n_bins):
+        sel = (R >= edges[k]) & (R < edges[k + 1])
+        cnt[k] = int(np.sum(sel))
+        if cnt[k] > 0:
+            avg[k] = np.mean(field[sel])
+            tot[k] = np.sum(field[sel])
+            tot_abs[k] = np.sum(np.abs(field[sel]))
+    return {"edges": edges, "r_bins": centres, "rho_avg": avg, "bin_sum": tot, "bin_abs": tot_abs, "bin_count": cnt,
+            "e_pos": full["e_pos"], "e_neg": full["e_neg"]}

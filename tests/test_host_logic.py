@@ -49,15 +49,40 @@ def test_reduce_table_is_fixed_order_and_exact_for_counts():
         table[r] = sharding.pack_row(e_pos, e_neg, cnt, 2, 3, [e_pos / 2, 1.0], [e_neg / 2, -1.0], [cnt // 2, 7])
         exp_pos += e_pos
         tot += cnt
-    out = sharding.reduce_table_host(table, 2, n_points=tot + 5 * nrows + 11)
+    out = sharding.reduce_table_host(table, 2, n_points=tot + 5 * nrows)
     assert out["e_pos"] == exp_pos                      # same left-to-right order
     assert out["cnt_pos"] == tot and out["cnt_neg"] == 2 * nrows and out["cnt_zero"] == 3 * nrows
-    assert out["cnt_nan"] == 11
+    assert out["cnt_nan"] == 0
     assert out["shell_cnt"][1] == 7 * nrows and len(out["shell_pos"]) == 2
     # splitting the rows between "ranks" and concatenating is the identity: P-independent by construction
     parts = np.concatenate([table[:10], table[10:37], table[37:]])
     assert sharding.reduce_table_host(parts, 2)["e_pos"] == out["e_pos"]
     assert ROW_WIDTH == 6 + 3 * MAX_SHELLS
+
+
+def test_non_finite_points_poison_the_sums_like_the_reference_masks():
+    """The reference multiplies by its masks (reproduce_rodal_exact.py:57-61, 220-224): NaN * 0 = inf * 0 = NaN."""
+    import math
+    e = np.array([1.0, -2.0, np.nan, 3.0])
+    with np.errstate(invalid="ignore"):
+        ref = (float(np.sum(e * (e > 0))), float(np.sum(e * (e < 0))))
+    assert all(math.isnan(v) for v in ref)
+    table = sharding.pack_row(4.0, -2.0, 2, 1, 0, [1.0], [-2.0], [3])[None, :]
+    out = sharding.reduce_table_host(table, 1, n_points=4)              # one point is none of pos / neg / zero
+    assert out["cnt_nan"] == 1
+    assert all(math.isnan(out[k]) for k in ("e_pos", "e_neg")) and math.isnan(out["shell_pos"][0])
+    # +inf inside shell 0, outside shell 1
+    e = np.array([1.0, -2.0, np.inf]); m0 = np.array([1, 1, 1]); m1 = np.array([1, 1, 0])
+    with np.errstate(invalid="ignore"):
+        ref = [float(np.sum(e * (e > 0))), float(np.sum(e * (e < 0))),
+               float(np.sum(e * (e > 0) * m0)), float(np.sum(e * (e > 0) * m1)), float(np.sum(e * (e < 0) * m0))]
+    res = {"cnt_nan": 0, "e_pos": math.inf, "e_neg": -2.0, "shell_pos": [math.inf, 1.0], "shell_neg": [-2.0, -2.0]}
+    sharding.apply_reference_nonfinite(res)
+    got = [res["e_pos"], res["e_neg"], res["shell_pos"][0], res["shell_pos"][1], res["shell_neg"][0]]
+    for g, r in zip(got, ref):
+        assert (math.isnan(g) and math.isnan(r)) or g == r, (got, ref)
+    fin = {"cnt_nan": 0, "e_pos": 1.0, "e_neg": -1.0, "shell_pos": [0.5], "shell_neg": [-0.5]}
+    assert sharding.apply_reference_nonfinite(dict(fin)) == fin
 
 
 def test_partition_points_round_robin():
@@ -119,3 +144,17 @@ def test_tail_fit_restatement():
     edges = np.linspace(0, R.max(), 31)
     sel = (R >= edges[-2]) & (R < edges[-1])
     assert avg.shape == (20,) and not sel[R == R.max()].any()
+
+
+def test_tail_integral_3d_algebra():
+    """4 pi A int_R^inf r^(2-n) dr = 4 pi A R^(3-n) / (n - 3) for n > 3; divergent otherwise (twin of tail.py:134-161)."""
+    from irrotational_warp_lab_b200 import tail
+    pos, neg = tail.tail_integral_3d(2.0, 6.0, 10.0)
+    assert neg == 0.0 and pos == pytest.approx(4.0 * np.pi * 2.0 * 10.0 ** -3 / 3.0, rel=1e-15)
+    pos, neg = tail.tail_integral_3d(-2.0, 6.0, 10.0)
+    assert pos == 0.0 and neg == pytest.approx(4.0 * np.pi * 2.0 * 10.0 ** -3 / 3.0, rel=1e-15)
+    assert tail.tail_integral_3d(1.0, 3.0, 10.0) == (0.0, 0.0)
+    # numerical quadrature of the same integrand
+    r = np.geomspace(10.0, 1e7, 200001)
+    f = 4.0 * np.pi * 2.0 * r ** (2.0 - 6.0)
+    assert float(np.sum(0.5 * (f[1:] + f[:-1]) * np.diff(r))) == pytest.approx(tail.tail_integral_3d(2.0, 6.0, 10.0)[0], rel=1e-6)
