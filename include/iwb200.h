@@ -17,6 +17,7 @@
  *                           + central_diff_2d      src/irrotational_warp/fd.py:6-25
  *                           + integrate_signed     src/irrotational_warp/adm.py:91-97
  *   iwb_radial_profile3d <- compute_radial_average_z0  src/irrotational_warp/tail.py:46-80 (its 3D generalisation)
+ *   iwb_einstein_z0      <- compute_einstein_eigenvalues  src/irrotational_warp/einstein.py:256-309
  *   iwb_energy3d_batch   <- the serial loops of sweep_velocity
  *                           scripts/sweep_superluminal.py:59-106 and grid_search
  *                           src/irrotational_warp/optimize.py:100-114
@@ -187,6 +188,29 @@ typedef struct {
 } iwb_slice_result;
 
 int iwb_slice_z0(iwb_handle *h, const iwb_params_slice *p, iwb_slice_result *out);
+
+/* Einstein-tensor eigenvalue diagnostic of the z = 0 slice (compute_einstein_eigenvalues,
+ * src/irrotational_warp/einstein.py:256-309, with its helpers :41-253): G^mu_nu of the metric built from the shift
+ * (beta_x, beta_y) -- host [ny, nx] doubles, e.g. the SliceResult fields -- and its four eigenvalues per grid point.
+ * Outputs are host buffers: eig_re / eig_im [4, ny, nx] (eigenvalue order is not LAPACK's; entry 3 is the decoupled
+ * G^3_3 = -R/2), eig_max and ricci_scalar [ny, nx], is_type_i [ny, nx] bytes (all |Im| < imag_tol; 1e-8 in the
+ * reference).  Parity with the reference is to rounding (its inverse and eigenvalues are LAPACK's), see DESIGN.md. */
+typedef struct {
+    int32_t nx, ny;
+    const double *beta_x, *beta_y;
+    double dx, dy;
+    double imag_tol;
+    double *eig_re, *eig_im;
+    double *eig_max, *ricci_scalar;
+    uint8_t *is_type_i;
+} iwb_params_einstein;
+
+typedef struct {
+    int64_t cnt_type_i;
+    double kernel_ms, total_ms;
+} iwb_einstein_result;
+
+int iwb_einstein_z0(iwb_handle *h, const iwb_params_einstein *p, iwb_einstein_result *out);
 
 /* Measured FP64 / FP32 FMA pipe peak of the handle's device (register-resident microbenchmark),
  * in TFLOP/s counting 2 flops per FMA; used as the roofline denominator by bench.py. */

@@ -86,6 +86,19 @@ class Profile3D(C.Structure):
                 ("count", C.POINTER(C.c_int64))]
 
 
+class ParamsEinstein(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32),
+                ("beta_x", C.POINTER(C.c_double)), ("beta_y", C.POINTER(C.c_double)),
+                ("dx", C.c_double), ("dy", C.c_double), ("imag_tol", C.c_double),
+                ("eig_re", C.POINTER(C.c_double)), ("eig_im", C.POINTER(C.c_double)),
+                ("eig_max", C.POINTER(C.c_double)), ("ricci_scalar", C.POINTER(C.c_double)),
+                ("is_type_i", C.POINTER(C.c_uint8))]
+
+
+class EinsteinResultC(C.Structure):
+    _fields_ = [("cnt_type_i", C.c_int64), ("kernel_ms", C.c_double), ("total_ms", C.c_double)]
+
+
 SYMBOLS = {
     "iwb_version": (C.c_int, []),
     "iwb_device_count": (C.c_int, []),
@@ -104,6 +117,7 @@ SYMBOLS = {
     "iwb_energy3d_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Params3D), C.POINTER(Result)]),
     "iwb_energy_axisym": (C.c_int, [C.c_void_p, C.POINTER(ParamsAxisym), C.POINTER(Result)]),
     "iwb_slice_z0": (C.c_int, [C.c_void_p, C.POINTER(ParamsSlice), C.POINTER(SliceResultC)]),
+    "iwb_einstein_z0": (C.c_int, [C.c_void_p, C.POINTER(ParamsEinstein), C.POINTER(EinsteinResultC)]),
     "iwb_measure_fma_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "iwb_selftest_divsqrt": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64),
                                        C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -31,6 +31,7 @@ UNITS = {
     "energy3d.cu": ["-fmad=false"] + ([f"-DIWB_DBG={os.environ['IWB_DBG']}"] if os.environ.get("IWB_DBG") else []) + ([f"-DIWB_BARRIER_BACKOFF_NS={os.environ['IWB_BACKOFF']}"] if os.environ.get("IWB_BACKOFF") else []),
     "energy3d_fast.cu": ["-fmad=true"],
     "planar.cu": ["-fmad=false"],
+    "einstein.cu": ["-fmad=false"],
 }
 
 

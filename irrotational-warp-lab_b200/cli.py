@@ -2,6 +2,9 @@
 
   * ``reproduce``  <- ``scripts/reproduce_rodal_exact.py`` ``main``  (/root/reference/scripts/reproduce_rodal_exact.py:244-341)
   * ``sweep``      <- ``scripts/sweep_superluminal.py`` ``main``     (/root/reference/scripts/sweep_superluminal.py:124-200)
+  * ``slice``      <- ``python -m irrotational_warp plot`` minus the image: the summary JSON of ``viz.plot_slice``
+                      (/root/reference/src/irrotational_warp/viz.py:30-105, flags of cli.py:16-25), with the optional
+                      ``--einstein`` and ``--tail-correction`` blocks
 
     python -m irrotational_warp_lab_b200.cli reproduce --mode 3d --n 256 --out results/repro.json
     python -m irrotational_warp_lab_b200.cli sweep --mode 3d --n 80 --v-steps 20 --out results/sweep.json
@@ -150,13 +153,61 @@ def sweep_main(argv=None) -> int:
     return 0
 
 
+def _array_summary(a):
+    """Arrays are summarised as in the reference's io._to_jsonable (io.py:15-21)."""
+    import numpy as np
+    return {"shape": list(a.shape), "min": float(np.min(a)), "max": float(np.max(a)), "mean": float(np.mean(a))}
+
+
+def slice_main(argv=None) -> int:
+    from .einstein import compute_einstein_eigenvalues
+    from .slice2d import compute_slice_z0, integrate_signed
+    p = argparse.ArgumentParser(description="z=0 slice diagnostic on the B200 engine (summary JSON of the reference's plot command)")
+    p.add_argument("--rho", type=float, default=10.0)
+    p.add_argument("--sigma", type=float, default=3.0)
+    p.add_argument("--v", type=float, default=1.5)
+    p.add_argument("--extent", type=float, default=20.0)
+    p.add_argument("--n", type=int, default=301)
+    p.add_argument("--einstein", action="store_true", help="Compute Einstein tensor eigenvalues")
+    p.add_argument("--tail-correction", action="store_true", help="Compute tail extrapolation for far-field decay")
+    p.add_argument("--json-out", type=str, default="results/summary.json")
+    args = p.parse_args(argv)
+    res = compute_slice_z0(rho=args.rho, sigma=args.sigma, v=args.v, extent=args.extent, n=args.n,
+                           tail_correction=args.tail_correction)
+    epos, eneg, enet = integrate_signed(res.rho_adm, dx=res.dx, dy=res.dy)
+    data = {
+        "params": {"rho": args.rho, "sigma": args.sigma, "v": args.v, "extent": args.extent, "n": args.n,
+                   "use_einstein": args.einstein, "use_tail_correction": args.tail_correction},
+        "integrals_2d": {"E_pos": epos, "E_neg": eneg, "E_net": enet},
+        "rho_adm": _array_summary(res.rho_adm),
+    }
+    t = res.tail_correction
+    if t is not None:                                           # viz.py:83-97
+        data["tail_correction"] = {
+            "exponent": t.exponent, "amplitude": t.amplitude, "fit_r_min": t.fit_r_min, "fit_r_max": t.fit_r_max,
+            "tail_integral_pos": t.tail_integral_pos, "tail_integral_neg": t.tail_integral_neg,
+            "tail_uncertainty": t.tail_uncertainty, "fit_residual_rms": t.fit_residual_rms,
+            "E_pos_corrected": epos + t.tail_integral_pos, "E_neg_corrected": eneg + t.tail_integral_neg,
+            "E_net_corrected": (epos + t.tail_integral_pos) - (eneg + t.tail_integral_neg),
+        }
+    if args.einstein:                                           # viz.py:36-37, 98-103
+        er = compute_einstein_eigenvalues(res.beta_x, res.beta_y, dx=res.dx, dy=res.dy)
+        data["einstein"] = {"eig_max": _array_summary(er.eig_max), "ricci_scalar": _array_summary(er.ricci_scalar),
+                            "type_i_fraction": float(er.is_type_i.sum()) / er.is_type_i.size}
+    _write_json(args.json_out, data)
+    print(f"Wrote JSON: {args.json_out}")
+    return 0
+
+
 def main(argv=None) -> int:
     argv = sys.argv[1:] if argv is None else argv
     if argv and argv[0] == "reproduce":
         return reproduce_main(argv[1:])
     if argv and argv[0] == "sweep":
         return sweep_main(argv[1:])
-    print("usage: python -m irrotational_warp_lab_b200.cli {reproduce|sweep} [options]", file=sys.stderr)
+    if argv and argv[0] == "slice":
+        return slice_main(argv[1:])
+    print("usage: python -m irrotational_warp_lab_b200.cli {reproduce|sweep|slice} [options]", file=sys.stderr)
     return 2
 
 

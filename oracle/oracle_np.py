@@ -350,3 +350,81 @@ def radial_profile_3d(*, rho, sigma, v, extent, n, n_bins=50, dtype="float64", i
             tot_abs[k] = np.sum(np.abs(field[sel]))
     return {"edges": edges, "r_bins": centres, "rho_avg": avg, "bin_sum": tot, "bin_abs": tot_abs, "bin_count": cnt,
             "e_pos": full["e_pos"], "e_neg": full["e_neg"]}
+
+
+# --------------------------------------------------------------------------- #
+# Einstein-tensor eigenvalue diagnostic on the z = 0 slice
+# --------------------------------------------------------------------------- #
+def einstein_eigenvalues(beta_x, beta_y, dx, dy):
+    """Restatement of compute_einstein_eigenvalues (/root/reference/src/irrotational_warp/einstein.py:256-309):
+    metric (:41-71), pointwise inverse (:74-93), Christoffel symbols from edge_order=1 differences (:96-164),
+    Ricci tensor and scalar (:167-226), mixed Einstein tensor (:229-253), eigenvalues, Type-I mask, max real part.
+    Array code over the grid instead of the reference's Python loops over points; the accumulation order of every
+    sum is the reference's, so everything up to the LAPACK calls is bit-identical (checked by make_golden.py)."""
+    beta_x = np.asarray(beta_x, dtype=np.float64)
+    beta_y = np.asarray(beta_y, dtype=np.float64)
+    ny, nx = beta_x.shape
+    g = np.zeros((4, 4, ny, nx))
+    g[0, 0] = -1.0 + beta_x ** 2 + beta_y ** 2
+    g[0, 1] = g[1, 0] = beta_x
+    g[0, 2] = g[2, 0] = beta_y
+    g[1, 1] = g[2, 2] = g[3, 3] = 1.0
+    # one LAPACK inverse per grid point (gufunc over the leading axes == the reference's per-point calls)
+    gi = np.moveaxis(np.linalg.inv(np.moveaxis(g, (0, 1), (2, 3))), (2, 3), (0, 1))
+
+    def d_dx(a):
+        return diff_axis(a, dx, 1, edge_order=1)
+
+    def d_dy(a):
+        return diff_axis(a, dy, 0, edge_order=1)
+
+    zero = 0.0
+    dg = {1: np.stack([np.stack([d_dx(g[a, b]) for b in range(4)]) for a in range(4)]),
+          2: np.stack([np.stack([d_dy(g[a, b]) for b in range(4)]) for a in range(4)])}
+
+    def dgc(direction, a, b):          # d_direction g_ab; the slice is stationary and z-independent
+        return dg[direction][a, b] if direction in dg else zero
+
+    gamma = np.zeros((4, 4, 4, ny, nx))
+    for mu in range(4):
+        for nu in range(4):
+            for al in range(4):
+                for sg in range(4):
+                    term = dgc(mu, sg, nu) + dgc(nu, sg, mu) - dgc(sg, mu, nu)
+                    gamma[al, mu, nu] += 0.5 * gi[al, sg] * term
+
+    ric = np.zeros((4, 4, ny, nx))
+    for mu in range(4):
+        for nu in range(4):
+            t1 = 0.0
+            t1 = t1 + d_dx(gamma[1, mu, nu])
+            t1 = t1 + d_dy(gamma[2, mu, nu])
+            t2 = 0.0
+            if nu in (1, 2):
+                dd = d_dx if nu == 1 else d_dy
+                for sg in range(4):
+                    t2 = t2 + dd(gamma[sg, mu, sg])
+            quad = 0.0
+            for sg in range(4):
+                for rh in range(4):
+                    quad = quad + (gamma[sg, rh, sg] * gamma[rh, mu, nu] - gamma[sg, rh, nu] * gamma[rh, mu, sg])
+            ric[mu, nu] = t1 - t2 + quad
+    scalar = np.zeros((ny, nx))
+    for mu in range(4):
+        for nu in range(4):
+            scalar += gi[mu, nu] * ric[mu, nu]
+
+    mixed = np.zeros((4, 4, ny, nx))
+    for mu in range(4):
+        for nu in range(4):
+            for sg in range(4):
+                mixed[mu, nu] += gi[mu, sg] * ric[sg, nu]
+    G = np.zeros_like(mixed)
+    for mu in range(4):
+        for nu in range(4):
+            G[mu, nu] = mixed[mu, nu] - 0.5 * (1.0 if mu == nu else 0.0) * scalar
+
+    eig = np.linalg.eigvals(np.moveaxis(G, (0, 1), (2, 3)))          # [ny, nx, 4]
+    eig_all = np.moveaxis(eig, 2, 0).astype(complex)
+    return {"eig_all": eig_all, "eig_max": np.max(eig_all.real, axis=0), "ricci_scalar": scalar,
+            "is_type_i": np.all(np.abs(eig_all.imag) < 1e-8, axis=0), "G_mixed": G, "gamma": gamma, "g_con": gi}

@@ -130,6 +130,27 @@ CASES_SLICE = [
 ]
 
 
+CASES_EINSTEIN = [
+    ("ein_plot_n41", dict(rho=10.0, sigma=3.0, v=1.5, extent=20.0, n=41)),
+    ("ein_plot_n101", dict(rho=10.0, sigma=3.0, v=1.5, extent=20.0, n=101)),
+    ("ein_subluminal_n61", dict(rho=5.0, sigma=4.0, v=0.5, extent=12.0, n=61)),
+    ("ein_minkowski_n21", dict(field="minkowski")),
+    ("ein_sine_n21", dict(field="sine")),
+]
+
+
+def einstein_test_field(kind):
+    """The two inputs of the reference's tests/test_einstein.py (flat space; a small harmonic shift)."""
+    n = 21
+    if kind == "minkowski":
+        return np.zeros((n, n)), np.zeros((n, n)), 0.5, 0.5
+    x = np.linspace(-5, 5, n)
+    X, _ = np.meshgrid(x, x)
+    d = float(x[1] - x[0])
+    bx = 0.01 * np.sin(2 * np.pi * X / 10.0)
+    return bx, np.zeros_like(bx), d, d
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--check-oracle", action="store_true")
@@ -205,11 +226,45 @@ def main(argv=None):
             assert oracle_np.integrate_signed(o["rho_adm"], o["dx"], o["dy"]) == (pos, neg, net)
             print("   oracle_np fields bit-equal: True")
 
+    # Einstein-tensor diagnostic (einstein.py): inputs are the reference's own slice fields and the two fields of
+    # the reference's tests/test_einstein.py
+    from irrotational_warp import einstein as ref_ein
+    outein = {}
+    for name, kw in CASES_EINSTEIN:
+        if args.only and args.only not in name:
+            continue
+        if "field" in kw:
+            bx, by, dx, dy = einstein_test_field(kw["field"])
+        else:
+            res = ref_adm.compute_slice_z0(**kw)
+            bx, by, dx, dy = res.beta_x, res.beta_y, res.dx, res.dy
+        er = ref_ein.compute_einstein_eigenvalues(bx, by, dx=dx, dy=dy)
+        eig_sorted = np.sort_complex(np.moveaxis(er.eig_all, 0, -1))           # [ny, nx, 4]
+        rec = {"params": kw, "dx": dx, "dy": dy, "shape": list(bx.shape),
+               "beta_x_sha256": hashlib.sha256(np.ascontiguousarray(bx).tobytes()).hexdigest(),
+               "beta_y_sha256": hashlib.sha256(np.ascontiguousarray(by).tobytes()).hexdigest(),
+               "type_i_count": int(er.is_type_i.sum()),
+               "ricci_abs_max": float(np.abs(er.ricci_scalar).max()),
+               "eig_max_abs_max": float(np.abs(er.eig_max).max()),
+               "ricci_scalar_samples": _samples(er.ricci_scalar, count=96),
+               "eig_max_samples": _samples(er.eig_max, count=96),
+               "eig_sorted_re_samples": _samples(np.ascontiguousarray(eig_sorted.real), count=96),
+               "eig_sorted_im_samples": _samples(np.ascontiguousarray(eig_sorted.imag), count=96),
+               "type_i_samples": _samples(er.is_type_i.astype(np.float64), count=96)}
+        outein[name] = rec
+        print(name, rec["type_i_count"], rec["ricci_abs_max"], rec["eig_max_abs_max"])
+        if args.check_oracle:
+            from oracle import oracle_np
+            o = oracle_np.einstein_eigenvalues(bx, by, dx, dy)
+            for fld in ("eig_all", "eig_max", "ricci_scalar", "is_type_i"):
+                assert np.array_equal(o[fld], getattr(er, fld), equal_nan=True), fld
+            print("   oracle_np einstein fields bit-equal: True")
+
     meta = {"numpy": np.__version__, "generator": "tests/golden/make_golden.py",
             "reference": "DawsonInstitute/irrotational-warp-lab (unmodified, NumPy path)"}
     if not args.only:
         for fname, payload in (("golden_3d.json", out3d), ("golden_axisym.json", outaxi),
-                               ("golden_slice.json", outslice)):
+                               ("golden_slice.json", outslice), ("golden_einstein.json", outein)):
             with open(os.path.join(HERE, fname), "w") as f:
                 json.dump({"meta": meta, "cases": payload}, f, indent=1, sort_keys=True)
             print("wrote", fname)
