@@ -4,7 +4,7 @@
 // point belongs to no bin) applied to the 3D field of compute_energy_3d instead of the z = 0 slice.
 //
 // The fused kernel emits rho for a slab of planes (8 B/point, the only time the field reaches HBM); k_radial_hist reads
-// it back once.  Deterministic by construction: a flush block of IWB_FLUSH_PLANES planes is split over PROF_SUB CTAs
+// it back once.  Deterministic by construction: a flush block of IWB_FLUSH_PLANES planes is split over PROF_SUB (64) CTAs
 // and PROF_NW warps by row index; every warp owns a private histogram that only its lane 0 updates, one bin at a time
 // (the lanes of one bin are added by a fixed shuffle tree); warps, CTAs and flush blocks are then added in index
 // order.  The result therefore depends neither on scheduling nor on how the planes were cut into passes or slabs.
@@ -14,7 +14,7 @@
 namespace iwb {
 
 constexpr int PROF_MAX_BINS = 256;
-constexpr int PROF_SUB = 8;       // CTAs per flush block
+constexpr int PROF_SUB = 64;      // CTAs per flush block (fixed: the summation order must not depend on the pass size)
 constexpr int PROF_NW = 8;        // warps per CTA
 
 struct ProfParams {
@@ -92,7 +92,18 @@ static __global__ void k_radial_reduce(const double* __restrict__ part_sum, cons
     if (q >= nb) return;
     double a = 0.0;
     long long c = 0;
-    for (size_t s = (size_t)fb0 * PROF_SUB; s < (size_t)fb1 * PROF_SUB; ++s) { a += part_sum[s * nb + q]; c += part_cnt[s * nb + q]; }
+    // PROF_SUB loads in flight, then added in index order (the order is what makes the result reproducible)
+    for (int fb = fb0; fb < fb1; ++fb) {
+        const size_t s0 = (size_t)fb * PROF_SUB;
+        for (int u = 0; u < PROF_SUB; u += 16) {
+            double v[16];
+            long long w[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { v[e] = part_sum[(s0 + u + e) * nb + q]; w[e] = part_cnt[(s0 + u + e) * nb + q]; }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { a += v[e]; c += w[e]; }
+        }
+    }
     sum[q] = a;
     cnt[q] = c;
 }
