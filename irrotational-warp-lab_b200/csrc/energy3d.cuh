@@ -182,7 +182,9 @@ k_energy3d(const __grid_constant__ K3Params P)
         // ---- accumulators (registers) -------------------------------------------------
         double acc_pos = 0.0, acc_neg = 0.0;
         double sh_pos[NSHA], sh_neg[NSHA];
-        int c_pos = 0, c_neg = 0, c_zero = 0;
+        int c_neg = 0;
+        int c_zn = 0;            // points that are neither positive nor negative: zeros in the low half, NaNs in the high half
+        int flush_from = 0;      // first plane of the running flush interval (set below)
         int sh_cnt[NSHA];
 #pragma unroll
         for (int s = 0; s < NSHA; ++s) { sh_pos[s] = 0.0; sh_neg[s] = 0.0; sh_cnt[s] = 0; }
@@ -302,12 +304,16 @@ k_energy3d(const __grid_constant__ K3Params P)
             const double ep1 = p1 ? e[1] : 0.0, en1 = n1 ? e[1] : 0.0;
             acc_pos += ep0; acc_neg += en0;
             acc_pos += ep1; acc_neg += en1;
-            if (p0) ++c_pos;
-            if (p1) ++c_pos;
-            if (n0) ++c_neg;
-            if (n1) ++c_neg;
-            if (out0 && (((__double2hiint(e[0]) & 0x7fffffff) | __double2loint(e[0])) == 0)) ++c_zero;
-            if (out1 && (((__double2hiint(e[1]) & 0x7fffffff) | __double2loint(e[1])) == 0)) ++c_zero;
+            // en is e where e < 0 and +0.0 elsewhere, so its sign bit IS the "negative" flag
+            c_neg += (int)((unsigned)__double2hiint(en0) >> 31) + (int)((unsigned)__double2hiint(en1) >> 31);
+            // Every output point is exactly one of pos / neg / zero / NaN.  Zeros and NaNs are rare (exact cancellation,
+            // overflow), so they are counted on a warp-uniform side path and the positive count is derived at the flush
+            // from the number of output points of the interval.
+            const bool o0 = out0 && !p0 && !n0, o1 = out1 && !p1 && !n1;
+            if (__any_sync(0xffffffffu, o0 || o1)) {
+                if (o0) c_zn += (e[0] == e[0]) ? 1 : 0x10000;
+                if (o1) c_zn += (e[1] == e[1]) ? 1 : 0x10000;
+            }
             if (NSH > 0) {
                 bool in0[NSHA], in1[NSHA];
                 bool any_in = false;
@@ -396,14 +402,14 @@ k_energy3d(const __grid_constant__ K3Params P)
         };
 
         // ---- block-level flush of the register sums into partial[fb][tile] ----------------
-        auto flush = [&](int fb) {
+        auto flush = [&](int fb, int i_last) {
             constexpr int NV = 6 + 3 * NSH;    // values actually reduced
             double vals[NV];
             vals[0] = acc_pos; vals[1] = acc_neg;
-            vals[2] = __longlong_as_double((long long)c_pos);
+            vals[2] = __longlong_as_double(0LL);      // cnt_pos: derived below from the other three
             vals[3] = __longlong_as_double((long long)c_neg);
-            vals[4] = __longlong_as_double((long long)c_zero);
-            vals[5] = __longlong_as_double(0LL);      // cnt_nan is derived on the host
+            vals[4] = __longlong_as_double((long long)(c_zn & 0xffff));
+            vals[5] = __longlong_as_double((long long)(c_zn >> 16));
 #pragma unroll
             for (int s = 0; s < NSH; ++s) {
                 vals[6 + s] = sh_pos[s];
@@ -436,7 +442,14 @@ k_energy3d(const __grid_constant__ K3Params P)
                     q = (sidx < NSH) ? 6 + grp * NSH + sidx : -1;
                 }
                 double acc = 0.0;
-                if (q >= 0) {
+                if (q == 2) {
+                    // positive points = output points of the interval - (negative + zero + NaN)
+                    long long rest = 0;
+                    for (int wv = 0; wv < NW; ++wv)
+                        rest += __double_as_longlong(scratch[wv * NV + 3]) + __double_as_longlong(scratch[wv * NV + 4]) +
+                                __double_as_longlong(scratch[wv * NV + 5]);
+                    acc = __longlong_as_double((long long)Tj * Tk * (i_last - flush_from + 1) - rest);
+                } else if (q >= 0) {
                     const bool is_int = (q >= 2 && q < 6) || (q >= 6 + 2 * NSH);
                     acc = scratch[q];
                     for (int wv = 1; wv < NW; ++wv) {
@@ -448,7 +461,8 @@ k_energy3d(const __grid_constant__ K3Params P)
                 P.partial[((size_t)fb * ntiles + tile) * ROW + slot] = acc;
             }
             // the scratch is rewritten at the next flush only, at least one step barrier from here
-            acc_pos = 0.0; acc_neg = 0.0; c_pos = c_neg = c_zero = 0;
+            acc_pos = 0.0; acc_neg = 0.0; c_neg = c_zn = 0;
+            flush_from = i_last + 1;
 #pragma unroll
             for (int s = 0; s < NSHA; ++s) { sh_pos[s] = 0.0; sh_neg[s] = 0.0; sh_cnt[s] = 0; }
         };
@@ -491,6 +505,7 @@ k_energy3d(const __grid_constant__ K3Params P)
 
         // ---- march: one (split) barrier per output plane -----------------------------------------------
         const int plim = min(P.n0 - 1, i1 + 1);          // phi(i1+1) is the last plane this item needs
+        flush_from = i0;
         int m3 = i0 % 3;                                 // i mod 3, kept incrementally (no division in the loop)
         for (int i = i0; i < i1; ++i) {
             const bool doP = produced < min(i + 3, plim);
@@ -516,7 +531,7 @@ k_energy3d(const __grid_constant__ K3Params P)
             step_wait();
             if (doP) ++produced;
             if (doL) px_last_done = true;
-            if (((i + 1) & (FLUSH - 1)) == 0 || i == i1 - 1) flush(i / FLUSH);
+            if (((i + 1) & (FLUSH - 1)) == 0 || i == i1 - 1) flush(i / FLUSH, i);
             m3 = m3p1;
         }
     }
