@@ -339,10 +339,13 @@ k_energy3d(const __grid_constant__ K3Params P)
                 if (__any_sync(0xffffffffu, any_in)) {
 #pragma unroll
                     for (int sh = 0; sh < NSH; ++sh) {
-                        sh_pos[sh] += in0[sh] ? ep0 : 0.0;
-                        sh_neg[sh] += in0[sh] ? en0 : 0.0;
-                        sh_pos[sh] += in1[sh] ? ep1 : 0.0;
-                        sh_neg[sh] += in1[sh] ? en1 : 0.0;
+                        // fma(e, m, acc) with m in {0, 1} rounds exactly like acc + (m ? e : 0): the mask multiply the
+                        // reference writes (e * (e > 0) * mask), one instruction per sum instead of a 64-bit select + add
+                        const double m0 = in0[sh] ? 1.0 : 0.0, m1 = in1[sh] ? 1.0 : 0.0;
+                        sh_pos[sh] = fma(ep0, m0, sh_pos[sh]);
+                        sh_neg[sh] = fma(en0, m0, sh_neg[sh]);
+                        sh_pos[sh] = fma(ep1, m1, sh_pos[sh]);
+                        sh_neg[sh] = fma(en1, m1, sh_neg[sh]);
                         if (in0[sh]) ++sh_cnt[sh];
                         if (in1[sh]) ++sh_cnt[sh];
                     }
