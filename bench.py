@@ -47,7 +47,7 @@ SLOTS_EXACT_ALG = 114.0
 CPU_SAMPLE_N = 256
 # dram__bytes_read.sum + dram__bytes_write.sum of k_energy3d, one launch at n = 1024^3 on one GPU, from the
 # committed `ncu --set full` capture of this command (profiles/r1_k_energy3d_n1024_final_summary.txt)
-NCU_DRAM_BYTES_PER_LAUNCH = 865024 + 768
+NCU_DRAM_BYTES_PER_LAUNCH = 486912 + 3328
 
 
 class ClockSampler:
