@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libiwb200.so")
+# IWB_LIB names another build of the same library in this directory (A/B timing of kernel variants; development aid)
+LIB_PATH = os.path.join(_HERE, os.path.basename(os.environ.get("IWB_LIB", "libiwb200.so")))
 
 MAX_SHELLS = 8
 FLUSH_PLANES = 16

@@ -124,6 +124,8 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
         else
             P.shell_thr[s] = -1.0;
     }
+    P.shell_thr_max = -1.0;
+    for (int s = 0; s < p->nshell; ++s) P.shell_thr_max = fmax(P.shell_thr_max, P.shell_thr[s]);
     const int nfb_total = (n0 + FLUSH - 1) / FLUSH;
     IWB_CUDA(partial.reserve((size_t)nfb_total * ntiles * ROW * sizeof(double)));
     P.partial = (double*)partial.p;

@@ -52,6 +52,7 @@ constexpr int ROW = IWB_ROW_WIDTH;  // doubles per partial row
 constexpr int FLUSH = IWB_FLUSH_PLANES;
 constexpr int SMEM_PAD = 8;         // guard doubles before and after the planes (lane 0 / lane 31 reads of idx -+ 1)
 constexpr int NPLANES = 11;
+constexpr int NEDGE = 18;           // one-sided coefficients a0 b0 c0 a1 b1 c1 of the three axes (shared-memory copy)
 
 struct K3Params {
     int n0, n1, n2;
@@ -67,6 +68,7 @@ struct K3Params {
     double dV;                     // (dx*dy)*dz
     double c16pi, rc16pi;          // 16.0*pi and RN(1/(16.0*pi))
     double shell_thr[IWB_MAX_SHELLS];   // r <= R  <=>  s <= shell_thr (s = r*r before sqrt), see host
+    double shell_thr_max;               // largest of them (row test of the shell sums)
     double* partial;               // [nfb_total][ntiles][ROW]
     double* rho_out;               // NULL or [i_end-i_begin][n1][n2]
     unsigned int* counter;         // dynamic work-item counter (0 at launch; reset by k_reduce_tiles)
@@ -81,7 +83,7 @@ struct Geo {
     static constexpr int TJ_MAX = RJ - 4;
     static constexpr int NT = NW * 32;
     static constexpr int SCRATCH = NW * ROW;     // block-reduction scratch (doubles)
-    static constexpr size_t SMEM_BYTES = (size_t(NPLANES) * PLANE + 2 * SMEM_PAD + RJ + SCRATCH) * sizeof(double);
+    static constexpr size_t SMEM_BYTES = (size_t(NPLANES) * PLANE + 2 * SMEM_PAD + RJ + SCRATCH + NEDGE) * sizeof(double);
 };
 
 template <int DT, int NSH, int RJ, int NW, bool EMIT, int MINB = 1, int MODE = 0>
@@ -98,6 +100,9 @@ k_energy3d(const __grid_constant__ K3Params P)
     double* const pz_buf = phi_ring + 9 * PLANE;           // 2 planes
     double* const yy_s = phi_ring + NPLANES * PLANE + SMEM_PAD;   // [RJ] y*y of the region rows
     double* const scratch = yy_s + RJ;                     // [NW][ROW]
+    // One-sided (global face) coefficients live in shared memory: only the edge flavours of the tasks read them,
+    // and as kernel parameters they would occupy 36 uniform registers that the interior loops need for their constants.
+    double* const ec_s = scratch + G::SCRATCH;             // [3][6]: x, y, z -> a0 b0 c0 a1 b1 c1
 
     const int tx = threadIdx.x & 31;
     const int ty = threadIdx.x >> 5;
@@ -105,12 +110,26 @@ k_energy3d(const __grid_constant__ K3Params P)
     const AxisCoef cx = P.cx, cy = P.cy, cz = P.cz;
     const PhiConst pc = P.pc;
 
+    // Interior (hot) loops address shared memory explicitly: byte address of this thread's first row in plane 0 of
+    // the phi ring, plus CTA-uniform plane offsets, plus immediates (iwb_device.cuh: lds_f64 / sts_f64).
+    constexpr unsigned PLB = PLANE * 8u;                   // bytes per plane
+    constexpr unsigned PXB = 3u * PLB, PYB = 7u * PLB;     // phi_x ring, phi_y buffers (phi_z buffers: PYB + 2 PLB)
+    constexpr int ROWB = NW * RK * 8;                      // bytes from a thread's row to its next row
+    const unsigned a_row0 = keep_u32((unsigned)__cvta_generic_to_shared(phi_ring) + (unsigned)(ty * RK + tx) * 8u);
+    const unsigned yy_row0 = keep_u32((unsigned)__cvta_generic_to_shared(yy_s) + (unsigned)ty * 8u);
+
     __shared__ int s_item;
     // Split (arrive / wait) barrier of the march: one mbarrier phase per output plane.
     __shared__ unsigned long long s_mbar;
     const unsigned mbar_addr = (unsigned)__cvta_generic_to_shared(&s_mbar);
     unsigned mbar_parity = 0;
     if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_addr), "r"(NW * 32));
+    if (threadIdx.x < NEDGE) {
+        // AxisCoef = {h2, rh2, a0, b0, c0, a1, b1, c1}; cx, cy, cz are consecutive members of K3Params
+        static_assert(sizeof(AxisCoef) == 8 * sizeof(double), "AxisCoef layout");
+        const int axis = threadIdx.x / 6, q = threadIdx.x - 6 * axis;
+        ec_s[threadIdx.x] = (&P.cx.h2)[8 * axis + 2 + q];
+    }
     __syncthreads();
     auto step_arrive = [&]() { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar_addr) : "memory"); };
     auto step_wait = [&]() {
@@ -179,15 +198,26 @@ k_energy3d(const __grid_constant__ K3Params P)
             cf1 = ((kb == 0) ? 2u : 0u) | ((kb == P.n2 - 1) ? 4u : 0u) | ((tx + 32 <= Tk + 1) ? 16u : 0u);
         }
 
+        // all-ones / zero words of the two columns: AND-mask of the energy density at non-output columns
+        const int om0 = (int)keep_u32((cf0 & 16u) ? 0xffffffffu : 0u), om1 = (int)keep_u32((cf1 & 16u) ? 0xffffffffu : 0u);
+        // smallest z*z among the tile's output columns (row test of the shell sums); every warp computes the same value
+        double zzmin_s;
+        {
+            double m = fmin((cf0 & 16u) ? zz0 : INFINITY, (cf1 & 16u) ? zz1 : INFINITY);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, off));
+            zzmin_s = m;
+        }
+
         // ---- accumulators (registers) -------------------------------------------------
-        double acc_pos = 0.0, acc_neg = 0.0;
-        double sh_pos[NSHA], sh_neg[NSHA];
-        int c_neg = 0;
-        int c_zn = 0;            // points that are neither positive nor negative: zeros in the low half, NaNs in the high half
+        double acc_sum = 0.0, acc_abs = 0.0;        // sum(e), sum(|e|) over the thread's output points
+        double sh_sum[NSHA], sh_abs[NSHA];
+        int cnt3 = 0;            // 8-bit fields: negative | positive << 8 | zero (incl. masked columns) << 16
         int flush_from = 0;      // first plane of the running flush interval (set below)
         int sh_cnt[NSHA];
 #pragma unroll
-        for (int s = 0; s < NSHA; ++s) { sh_pos[s] = 0.0; sh_neg[s] = 0.0; sh_cnt[s] = 0; }
+        for (int s = 0; s < NSHA; ++s) { sh_sum[s] = 0.0; sh_abs[s] = 0.0; sh_cnt[s] = 0; }
+        static_assert(2 * ((RJ + NW - 1) / NW) * FLUSH <= 255, "count fields of cnt3 are 8 bits wide");
 
         const int w0 = min(max(i0 - 1, 0), P.n0 - 3);
         const int pstart = max(0, w0 - 1);
@@ -198,16 +228,16 @@ k_energy3d(const __grid_constant__ K3Params P)
         auto dZ = [&](const double* B, int idx, unsigned cf, auto edge_tag) -> double {
             double d = cdivm<MODE>(B[idx + 1] - B[idx - 1], cz.h2, cz.rh2);
             if (decltype(edge_tag)::value) {
-                if (cf & 2u) d = edge3(cz.a0, B[idx], cz.b0, B[idx + 1], cz.c0, B[idx + 2]);
-                else if (cf & 4u) d = edge3(cz.a1, B[idx - 2], cz.b1, B[idx - 1], cz.c1, B[idx]);
+                if (cf & 2u) d = edge3(ec_s[12], B[idx], ec_s[13], B[idx + 1], ec_s[14], B[idx + 2]);
+                else if (cf & 4u) d = edge3(ec_s[15], B[idx - 2], ec_s[16], B[idx - 1], ec_s[17], B[idx]);
             }
             return d;
         };
         // jedge: 0 interior, 1 row j == 0, 2 row j == n1-1 (warp-uniform)
         auto dY = [&](const double* B, int idx, int jedge, auto edge_tag) -> double {
             if (decltype(edge_tag)::value) {
-                if (jedge == 1) return edge3(cy.a0, B[idx], cy.b0, B[idx + RK], cy.c0, B[idx + 2 * RK]);
-                if (jedge == 2) return edge3(cy.a1, B[idx - 2 * RK], cy.b1, B[idx - RK], cy.c1, B[idx]);
+                if (jedge == 1) return edge3(ec_s[6], B[idx], ec_s[7], B[idx + RK], ec_s[8], B[idx + 2 * RK]);
+                if (jedge == 2) return edge3(ec_s[9], B[idx - 2 * RK], ec_s[10], B[idx - RK], ec_s[11], B[idx]);
             }
             return cdivm<MODE>(B[idx + RK] - B[idx - RK], cy.h2, cy.rh2);
         };
@@ -250,8 +280,8 @@ k_energy3d(const __grid_constant__ K3Params P)
                     px_w[base + 32] = cdivm<MODE>(f[1] - ph_m2[base + 32], cx.h2, cx.rh2);
                 }
                 if (EDGE && do_px0) {
-                    px_ring[base] = edge3(cx.a0, ph_m2[base], cx.b0, ph_m1[base], cx.c0, f[0]);
-                    px_ring[base + 32] = edge3(cx.a0, ph_m2[base + 32], cx.b0, ph_m1[base + 32], cx.c0, f[1]);
+                    px_ring[base] = edge3(ec_s[0], ph_m2[base], ec_s[1], ph_m1[base], ec_s[2], f[0]);
+                    px_ring[base + 32] = edge3(ec_s[0], ph_m2[base + 32], ec_s[1], ph_m1[base + 32], ec_s[2], f[1]);
                 }
             }
         };
@@ -267,8 +297,8 @@ k_energy3d(const __grid_constant__ K3Params P)
             for (int jr = ty; jr <= jr_hi; jr += NW) {
                 if (jr < jr_lo) continue;
                 const int base = jr * RK + tx;
-                px_w[base] = edge3(cx.a1, ph_m2[base], cx.b1, ph_m1[base], cx.c1, ph_p[base]);
-                px_w[base + 32] = edge3(cx.a1, ph_m2[base + 32], cx.b1, ph_m1[base + 32], cx.c1, ph_p[base + 32]);
+                px_w[base] = edge3(ec_s[3], ph_m2[base], ec_s[4], ph_m1[base], ec_s[5], ph_p[base]);
+                px_w[base + 32] = edge3(ec_s[3], ph_m2[base + 32], ec_s[4], ph_m1[base + 32], ec_s[5], ph_p[base + 32]);
             }
         };
 
@@ -291,63 +321,57 @@ k_energy3d(const __grid_constant__ K3Params P)
             }
         };
 
-        // ---- predicated sums of one row's two points (reproduce_rodal_exact.py:57-61, 220-224) ------
-        // NaN points are not counted here: every point is exactly one of pos / neg / zero / NaN, so the
-        // host derives cnt_nan from the number of points.  The shell sums are skipped for a warp none of
-        // whose lanes lies inside any shell (adding +0.0 is the identity, so this does not change a
-        // single bit of the result).
+        // ---- sums of one row's two points (reproduce_rodal_exact.py:57-61, 220-224) ---------------------
+        // e is masked to +0.0 at the non-output columns (an AND with the column's all-ones / zero word), and the
+        // accumulators are sum(e) and sum(|e|): E+ = (sum + sum|.|)/2, E- = (sum - sum|.|)/2, formed per thread at the
+        // flush.  The shell sums use the reference's own mask multiply, fma(e, m, acc) with m in {0, 1}.  A NaN or an
+        // infinite point therefore poisons exactly the sums it poisons in the reference (NaN * 0 = inf * 0 = NaN).
+        // Counts: every point is exactly one of neg / pos / zero / NaN; the first three are counted here in 8-bit
+        // fields of one register (<= 64 points per thread and flush interval), NaN is derived by the host.  The zero
+        // field also counts the masked non-output columns; the flush subtracts their (known) number.
         auto tally2 = [&](const double (&e)[2], double yyj, double xxi) {
-            const bool out0 = (cf0 & 16u) != 0, out1 = (cf1 & 16u) != 0;
-            const bool p0 = out0 && (e[0] > 0.0), n0 = out0 && (e[0] < 0.0);
-            const bool p1 = out1 && (e[1] > 0.0), n1 = out1 && (e[1] < 0.0);
-            const double ep0 = p0 ? e[0] : 0.0, en0 = n0 ? e[0] : 0.0;
-            const double ep1 = p1 ? e[1] : 0.0, en1 = n1 ? e[1] : 0.0;
-            acc_pos += ep0; acc_neg += en0;
-            acc_pos += ep1; acc_neg += en1;
-            // en is e where e < 0 and +0.0 elsewhere, so its sign bit IS the "negative" flag
-            c_neg += (int)((unsigned)__double2hiint(en0) >> 31) + (int)((unsigned)__double2hiint(en1) >> 31);
-            // Every output point is exactly one of pos / neg / zero / NaN.  Zeros and NaNs are rare (exact cancellation,
-            // overflow), so they are counted on a warp-uniform side path and the positive count is derived at the flush
-            // from the number of output points of the interval.
-            const bool o0 = out0 && !p0 && !n0, o1 = out1 && !p1 && !n1;
-            if (__any_sync(0xffffffffu, o0 || o1)) {
-                if (o0) c_zn += (e[0] == e[0]) ? 1 : 0x10000;
-                if (o1) c_zn += (e[1] == e[1]) ? 1 : 0x10000;
-            }
+            const double em0 = __hiloint2double(__double2hiint(e[0]) & om0, __double2loint(e[0]) & om0);
+            const double em1 = __hiloint2double(__double2hiint(e[1]) & om1, __double2loint(e[1]) & om1);
+            acc_sum += em0; acc_abs += fabs(em0);
+            acc_sum += em1; acc_abs += fabs(em1);
+            if (em0 < 0.0) cnt3 += 1;
+            if (em1 < 0.0) cnt3 += 1;
+            if (em0 > 0.0) cnt3 += 0x100;
+            if (em1 > 0.0) cnt3 += 0x100;
+            if (((__double2hiint(em0) & 0x7fffffff) | __double2loint(em0)) == 0) cnt3 += 0x10000;
+            if (((__double2hiint(em1) & 0x7fffffff) | __double2loint(em1)) == 0) cnt3 += 0x10000;
             if (NSH > 0) {
-                bool in0[NSHA], in1[NSHA];
-                bool any_in = false;
+                // Row test first: s = RN(sxy + zz) is monotone in zz, so if even the tile's smallest zz lies outside
+                // the largest shell, no column of this row is inside any shell (all lanes agree: uniform branch).
                 if (DT == IWB_F64) {
                     const double sxy = xxi + yyj;
+                    if (sxy + zzmin_s > P.shell_thr_max) return;
                     const double s0 = sxy + zz0, s1 = sxy + zz1;
 #pragma unroll
                     for (int sh = 0; sh < NSH; ++sh) {
-                        in0[sh] = out0 && (s0 <= P.shell_thr[sh]);
-                        in1[sh] = out1 && (s1 <= P.shell_thr[sh]);
-                        any_in |= in0[sh] | in1[sh];
+                        const bool in0 = (s0 <= P.shell_thr[sh]), in1 = (s1 <= P.shell_thr[sh]);
+                        const double m0 = in0 ? 1.0 : 0.0, m1 = in1 ? 1.0 : 0.0;
+                        sh_sum[sh] = fma(em0, m0, sh_sum[sh]);
+                        sh_abs[sh] = fma(fabs(em0), m0, sh_abs[sh]);
+                        sh_sum[sh] = fma(em1, m1, sh_sum[sh]);
+                        sh_abs[sh] = fma(fabs(em1), m1, sh_abs[sh]);
+                        if (in0 && om0) ++sh_cnt[sh];
+                        if (in1 && om1) ++sh_cnt[sh];
                     }
                 } else {
                     const float sxy = __fadd_rn((float)xxi, (float)yyj);
+                    if (__fadd_rn(sxy, (float)zzmin_s) > (float)P.shell_thr_max) return;
                     const float s0 = __fadd_rn(sxy, (float)zz0), s1 = __fadd_rn(sxy, (float)zz1);
 #pragma unroll
                     for (int sh = 0; sh < NSH; ++sh) {
-                        in0[sh] = out0 && (s0 <= (float)P.shell_thr[sh]);
-                        in1[sh] = out1 && (s1 <= (float)P.shell_thr[sh]);
-                        any_in |= in0[sh] | in1[sh];
-                    }
-                }
-                if (__any_sync(0xffffffffu, any_in)) {
-#pragma unroll
-                    for (int sh = 0; sh < NSH; ++sh) {
-                        // fma(e, m, acc) with m in {0, 1} rounds exactly like acc + (m ? e : 0): the mask multiply the
-                        // reference writes (e * (e > 0) * mask), one instruction per sum instead of a 64-bit select + add
-                        const double m0 = in0[sh] ? 1.0 : 0.0, m1 = in1[sh] ? 1.0 : 0.0;
-                        sh_pos[sh] = fma(ep0, m0, sh_pos[sh]);
-                        sh_neg[sh] = fma(en0, m0, sh_neg[sh]);
-                        sh_pos[sh] = fma(ep1, m1, sh_pos[sh]);
-                        sh_neg[sh] = fma(en1, m1, sh_neg[sh]);
-                        if (in0[sh]) ++sh_cnt[sh];
-                        if (in1[sh]) ++sh_cnt[sh];
+                        const bool in0 = (s0 <= (float)P.shell_thr[sh]), in1 = (s1 <= (float)P.shell_thr[sh]);
+                        const double m0 = in0 ? 1.0 : 0.0, m1 = in1 ? 1.0 : 0.0;
+                        sh_sum[sh] = fma(em0, m0, sh_sum[sh]);
+                        sh_abs[sh] = fma(fabs(em0), m0, sh_abs[sh]);
+                        sh_sum[sh] = fma(em1, m1, sh_sum[sh]);
+                        sh_abs[sh] = fma(fabs(em1), m1, sh_abs[sh]);
+                        if (in0 && om0) ++sh_cnt[sh];
+                        if (in1 && om1) ++sh_cnt[sh];
                     }
                 }
             }
@@ -376,9 +400,9 @@ k_energy3d(const __grid_constant__ K3Params P)
                     const unsigned cf = a ? cf1 : cf0;
                     double pxx;
                     if (EDGE && iedge == 1)        // phi_x(0), (1), (2)
-                        pxx = edge3(cx.a0, px_i[idx], cx.b0, px_p[idx], cx.c0, px_m2[idx]);
+                        pxx = edge3(ec_s[0], px_i[idx], ec_s[1], px_p[idx], ec_s[2], px_m2[idx]);
                     else if (EDGE && iedge == 2)   // phi_x(n0-3), (n0-2), (n0-1)
-                        pxx = edge3(cx.a1, px_m2[idx], cx.b1, px_m[idx], cx.c1, px_i[idx]);
+                        pxx = edge3(ec_s[3], px_m2[idx], ec_s[4], px_m[idx], ec_s[5], px_i[idx]);
                     else
                         pxx = cdivm<MODE>(px_p[idx] - px_m[idx], cx.h2, cx.rh2);
                     const double pxy = dY(px_i, idx, jedge, edge_tag);
@@ -404,19 +428,140 @@ k_energy3d(const __grid_constant__ K3Params P)
             }
         };
 
+        // ================= interior flavours of the tasks (no global face in reach) =========================
+        // Same arithmetic as taskO / taskC / taskP with EDGE = false, written against explicit shared-memory
+        // addresses: per row one base register per plane and immediates for the neighbours, all loads of a row
+        // issued before its arithmetic, stores last.  O(i) and C(q) share the row loop (they read and write
+        // disjoint planes), so the short dependent chains of C fill the gaps of O.
+        auto stepOC_fast = [&](bool doO, int i, double xxi, bool doC, int q, int s3q) {
+            // CTA-uniform plane offsets of this step (kept: computed once per step, not once per row)
+            const unsigned o_pxi = keep_u32(PXB + (unsigned)(i & 3) * PLB);
+            const unsigned o_pxp = keep_u32(PXB + (unsigned)((i + 1) & 3) * PLB);      // phi_x(i+1)
+            const unsigned o_pxm = keep_u32(PXB + (unsigned)((i + 3) & 3) * PLB);      // phi_x(i-1)
+            const unsigned o_py = keep_u32(PYB + (unsigned)(i & 1) * PLB);             // phi_y(i); phi_z(i) at + 2 PLB
+            const unsigned o_ph = keep_u32((unsigned)s3q * PLB);                       // phi(q)
+            const unsigned o_w = keep_u32(PYB + (unsigned)(q & 1) * PLB);              // phi_y(q); phi_z(q) at + 2 PLB
+            constexpr int R8 = RK * 8, ZB = 2 * (int)PLB;
+            unsigned A = a_row0, ya = yy_row0;
+#pragma unroll 1
+            for (int jr = ty; jr < RJ; jr += NW, A += ROWB, ya += NW * 8) {
+                if (doO && jr >= 2 && jr <= Tj + 1) {
+                    const unsigned Ai = A + o_pxi, Ap = A + o_pxp, Am = A + o_pxm, Ay = A + o_py;
+                    // column a = this lane, column b = lane + 32 (256 bytes further)
+                    const double xpa = lds_f64<0>(Ap), xma = lds_f64<0>(Am);
+                    const double xpb = lds_f64<256>(Ap), xmb = lds_f64<256>(Am);
+                    const double xjpa = lds_f64<R8>(Ai), xjma = lds_f64<-R8>(Ai);
+                    const double xjpb = lds_f64<256 + R8>(Ai), xjmb = lds_f64<256 - R8>(Ai);
+                    const double xkpa = lds_f64<8>(Ai), xkma = lds_f64<-8>(Ai);
+                    const double xkpb = lds_f64<256 + 8>(Ai), xkmb = lds_f64<256 - 8>(Ai);
+                    const double yjpa = lds_f64<R8>(Ay), yjma = lds_f64<-R8>(Ay);
+                    const double yjpb = lds_f64<256 + R8>(Ay), yjmb = lds_f64<256 - R8>(Ay);
+                    const double ykpa = lds_f64<8>(Ay), ykma = lds_f64<-8>(Ay);
+                    const double ykpb = lds_f64<256 + 8>(Ay), ykmb = lds_f64<256 - 8>(Ay);
+                    const double zkpa = lds_f64<ZB + 8>(Ay), zkma = lds_f64<ZB - 8>(Ay);
+                    const double zkpb = lds_f64<ZB + 256 + 8>(Ay), zkmb = lds_f64<ZB + 256 - 8>(Ay);
+                    const double yyj = lds_f64<0>(ya);
+                    const double dpx[2] = {xpa - xma, xpb - xmb}, dxy[2] = {xjpa - xjma, xjpb - xjmb};
+                    const double dxz[2] = {xkpa - xkma, xkpb - xkmb}, dyy[2] = {yjpa - yjma, yjpb - yjmb};
+                    const double dyz[2] = {ykpa - ykma, ykpb - ykmb}, dzz[2] = {zkpa - zkma, zkpb - zkmb};
+                    double rho2[2];
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const double pxx = cdivm<MODE>(dpx[a], cx.h2, cx.rh2);
+                        const double pxy = cdivm<MODE>(dxy[a], cy.h2, cy.rh2);
+                        const double pxz = cdivm<MODE>(dxz[a], cz.h2, cz.rh2);
+                        const double pyy = cdivm<MODE>(dyy[a], cy.h2, cy.rh2);
+                        const double pyz = cdivm<MODE>(dyz[a], cz.h2, cz.rh2);
+                        const double pzz = cdivm<MODE>(dzz[a], cz.h2, cz.rh2);
+                        const double tr = (pxx + pyy) + pzz;
+                        const double diag = (pxx * pxx + pyy * pyy) + pzz * pzz;
+                        const double off = (pxy * pxy + pxz * pxz) + pyz * pyz;
+                        const double kk = fma(2.0, off, diag);
+                        rho2[a] = cdivm<MODE>(tr * tr - kk, P.c16pi, P.rc16pi);
+                    }
+                    if (EMIT) {
+                        const long long j = j0 - 2 + jr, k = k0 - 2 + tx;
+                        double* dst = P.rho_out + ((long long)(i - P.i_begin) * P.n1 + j) * P.n2 + k;
+                        if (cf0 & 16u) dst[0] = rho2[0];
+                        if (cf1 & 16u) dst[32] = rho2[1];
+                    }
+                    const double e2[2] = {rho2[0] * P.dV, rho2[1] * P.dV};
+                    tally2(e2, yyj, xxi);
+                }
+                if (doC && jr >= py_lo && jr <= py_hi) {
+                    const unsigned Ah = A + o_ph, Aw = A + o_w;
+                    const bool z_row = (jr >= 2 && jr <= Tj + 1);
+                    const double hjpa = lds_f64<R8>(Ah), hjma = lds_f64<-R8>(Ah);
+                    const double hjpb = lds_f64<256 + R8>(Ah), hjmb = lds_f64<256 - R8>(Ah);
+                    const double hkpa = lds_f64<8>(Ah), hkma = lds_f64<-8>(Ah);
+                    const double hkpb = lds_f64<256 + 8>(Ah), hkmb = lds_f64<256 - 8>(Ah);
+                    const double pya = cdivm<MODE>(hjpa - hjma, cy.h2, cy.rh2);
+                    const double pyb = cdivm<MODE>(hjpb - hjmb, cy.h2, cy.rh2);
+                    const double pza = cdivm<MODE>(hkpa - hkma, cz.h2, cz.rh2);
+                    const double pzb = cdivm<MODE>(hkpb - hkmb, cz.h2, cz.rh2);
+                    sts_f64<0>(Aw, pya);
+                    sts_f64<256>(Aw, pyb);
+                    if (z_row) {
+                        sts_f64<ZB>(Aw, pza);
+                        sts_f64<ZB + 256>(Aw, pzb);
+                    }
+                }
+            }
+        };
+
+        // P(p) for an interior tile: phi(p) at the own columns and phi_x(p-1) = (phi(p) - phi(p-2)) / 2dx
+        auto taskP_fast = [&](int p, int s3 /* p mod 3 */, double xp, double xxp) {
+            const int s3m2 = (s3 == 2) ? 0 : s3 + 1;
+            const unsigned o_p = keep_u32((unsigned)s3 * PLB);                         // phi(p)
+            const unsigned o_m2 = keep_u32((unsigned)s3m2 * PLB);                      // phi(p-2)
+            const unsigned o_xw = keep_u32(PXB + (unsigned)((p + 3) & 3) * PLB);       // phi_x(p-1)
+            const bool do_px = (p - 2 >= pstart);
+            unsigned A = a_row0, ya = yy_row0;
+#pragma unroll 1
+            for (int jr = ty; jr <= jr_hi; jr += NW, A += ROWB, ya += NW * 8) {
+                if (jr < jr_lo) continue;
+                const unsigned Am2 = A + o_m2;
+                const double yyj = lds_f64<0>(ya);
+                const double m2a = lds_f64<0>(Am2), m2b = lds_f64<256>(Am2);   // harmless when !do_px (never used)
+                double f[2];
+                if (IWB_DBG & 2) { f[0] = xxp + zz0; f[1] = xxp + zz1; }
+                else if (DT == IWB_F64) {
+                    const double sxy = xxp + yyj;
+                    const double s[2] = {sxy + zz0, sxy + zz1};
+                    const bool origin_row = (p == P.i_zero) && (j0 - 2 + jr == P.j_zero);
+                    if (MODE == 0) phi_exact_f64<2, true>(s, xp, pc, f, origin_row || !pc.prechecked);
+                    else phi_fast_f64<2>(s, xp, pc, f, origin_row || !pc.prechecked);
+                } else {
+                    const float sxy = __fadd_rn((float)xxp, (float)yyj);
+                    const float s[2] = {__fadd_rn(sxy, (float)zz0), __fadd_rn(sxy, (float)zz1)};
+                    const bool origin_row = (p == P.i_zero) && (j0 - 2 + jr == P.j_zero);
+                    phi_exact_f32ref<2, true>(s, (float)xp, pc, f, origin_row || !pc.prechecked);
+                }
+                const unsigned Ap = A + o_p;
+                sts_f64<0>(Ap, f[0]);
+                sts_f64<256>(Ap, f[1]);
+                if (do_px) {
+                    const unsigned Ax = A + o_xw;
+                    sts_f64<0>(Ax, cdivm<MODE>(f[0] - m2a, cx.h2, cx.rh2));
+                    sts_f64<256>(Ax, cdivm<MODE>(f[1] - m2b, cx.h2, cx.rh2));
+                }
+            }
+        };
+
         // ---- block-level flush of the register sums into partial[fb][tile] ----------------
         auto flush = [&](int fb, int i_last) {
             constexpr int NV = 6 + 3 * NSH;    // values actually reduced
             double vals[NV];
-            vals[0] = acc_pos; vals[1] = acc_neg;
-            vals[2] = __longlong_as_double(0LL);      // cnt_pos: derived below from the other three
-            vals[3] = __longlong_as_double((long long)c_neg);
-            vals[4] = __longlong_as_double((long long)(c_zn & 0xffff));
-            vals[5] = __longlong_as_double((long long)(c_zn >> 16));
+            // E+ = (sum + sum|.|)/2 and E- = (sum - sum|.|)/2, per thread (halving is exact)
+            vals[0] = (acc_sum + acc_abs) * 0.5; vals[1] = (acc_sum - acc_abs) * 0.5;
+            vals[2] = __longlong_as_double((long long)((cnt3 >> 8) & 0xff));
+            vals[3] = __longlong_as_double((long long)(cnt3 & 0xff));
+            vals[4] = __longlong_as_double((long long)((cnt3 >> 16) & 0xff));   // zeros + masked columns (corrected below)
+            vals[5] = __longlong_as_double(0LL);      // cnt_nan: derived by the host from the other three
 #pragma unroll
             for (int s = 0; s < NSH; ++s) {
-                vals[6 + s] = sh_pos[s];
-                vals[6 + NSH + s] = sh_neg[s];
+                vals[6 + s] = (sh_sum[s] + sh_abs[s]) * 0.5;
+                vals[6 + NSH + s] = (sh_sum[s] - sh_abs[s]) * 0.5;
                 vals[6 + 2 * NSH + s] = __longlong_as_double((long long)sh_cnt[s]);
             }
             // warp butterfly (fixed order), integers added as integers
@@ -445,14 +590,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                     q = (sidx < NSH) ? 6 + grp * NSH + sidx : -1;
                 }
                 double acc = 0.0;
-                if (q == 2) {
-                    // positive points = output points of the interval - (negative + zero + NaN)
-                    long long rest = 0;
-                    for (int wv = 0; wv < NW; ++wv)
-                        rest += __double_as_longlong(scratch[wv * NV + 3]) + __double_as_longlong(scratch[wv * NV + 4]) +
-                                __double_as_longlong(scratch[wv * NV + 5]);
-                    acc = __longlong_as_double((long long)Tj * Tk * (i_last - flush_from + 1) - rest);
-                } else if (q >= 0) {
+                if (q >= 0) {
                     const bool is_int = (q >= 2 && q < 6) || (q >= 6 + 2 * NSH);
                     acc = scratch[q];
                     for (int wv = 1; wv < NW; ++wv) {
@@ -460,28 +598,40 @@ k_energy3d(const __grid_constant__ K3Params P)
                         if (is_int) acc = __longlong_as_double(__double_as_longlong(acc) + __double_as_longlong(o));
                         else acc += o;
                     }
+                    // the zero field counted the masked (non-output) columns of every row as well
+                    if (q == 4)
+                        acc = __longlong_as_double(__double_as_longlong(acc) -
+                                                   (long long)Tj * (RK - Tk) * (i_last - flush_from + 1));
                 }
                 P.partial[((size_t)fb * ntiles + tile) * ROW + slot] = acc;
             }
             // the scratch is rewritten at the next flush only, at least one step barrier from here
-            acc_pos = 0.0; acc_neg = 0.0; c_neg = c_zn = 0;
+            acc_sum = 0.0; acc_abs = 0.0; cnt3 = 0;
             flush_from = i_last + 1;
 #pragma unroll
-            for (int s = 0; s < NSHA; ++s) { sh_pos[s] = 0.0; sh_neg[s] = 0.0; sh_cnt[s] = 0; }
+            for (int s = 0; s < NSHA; ++s) { sh_sum[s] = 0.0; sh_abs[s] = 0.0; sh_cnt[s] = 0; }
         };
 
         auto runP = [&](int p, int s3, double xp, double xxp) {
             if (tile_edge || (p == 2 && pstart == 0)) taskP(p, s3, xp, xxp, std::true_type{});
-            else taskP(p, s3, xp, xxp, std::false_type{});
+            else taskP_fast(p, s3, xp, xxp);
         };
         auto runC = [&](int q, int s3) {
             if (tile_edge) taskC(q, s3, std::true_type{});
-            else taskC(q, s3, std::false_type{});
+            else stepOC_fast(false, 0, 0.0, true, q, s3);
         };
-        auto runO = [&](int i, double xxi) {
-            if (IWB_DBG & 1) return;
-            if (tile_edge || i == 0 || i == P.n0 - 1) taskO(i, xxi, std::true_type{});
-            else taskO(i, xxi, std::false_type{});
+        // O(i) followed by C(i+1) (the latter when doC)
+        auto runOC = [&](int i, double xxi, bool doC, int m3p1) {
+            const bool doO = !(IWB_DBG & 1);
+            if (tile_edge) {
+                if (doO) taskO(i, xxi, std::true_type{});
+                if (doC) taskC(i + 1, m3p1, std::true_type{});
+            } else if (i == 0 || i == P.n0 - 1) {       // interior tile, one-sided plane of axis 0
+                if (doO) taskO(i, xxi, std::true_type{});
+                if (doC) stepOC_fast(false, 0, 0.0, true, i + 1, m3p1);
+            } else {
+                stepOC_fast(doO, i, xxi, doC, i + 1, m3p1);
+            }
         };
         // phi_x(n0-1) may be written once every phi plane exists and its ring slot (that of phi_x(n0-5),
         // last read by O(n0-4)) is dead, i.e. from the step of output plane n0-3 on; it is first needed
@@ -522,8 +672,7 @@ k_energy3d(const __grid_constant__ K3Params P)
             // and C(i+1) (phi_y/phi_z(i+1) for their O(i+1); phi(i+1) dead for their P(i+4)).  Task P touches only ring
             // entries of the own columns until two steps later (tasks P and O assign rows to warps identically), so it
             // runs between the arrival and the wait: the barrier latency and the imbalance of O/C hide behind it.
-            runO(i, xxi);
-            if (doC) runC(i + 1, m3p1);
+            runOC(i, xxi, doC, m3p1);
             step_arrive();
             if (doP) {
                 // steady state: produced + 1 == i + 3, whose slot is i mod 3; otherwise (start / end of the axis) compute it
