@@ -17,8 +17,12 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_obj")
-LIB = os.path.join(HERE, "libiwb200.so")
+# IWB_VARIANT=name + IWB_EXTRA_FLAGS="-DX=1 ..." build libiwb200_name.so beside the product library (A/B timing of
+# kernel variants on one GPU box, selected at run time with IWB_LIB; development aid)
+VARIANT = os.environ.get("IWB_VARIANT", "")
+OBJ = os.path.join(HERE, "_obj" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "libiwb200" + ("_" + VARIANT if VARIANT else "") + ".so")
+EXTRA = os.environ.get("IWB_EXTRA_FLAGS", "").split()
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -50,7 +54,7 @@ def _stale(target, sources):
 def _compile(unit, flags, verbose):
     src = os.path.join(CSRC, unit)
     obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
-    cmd = [NVCC, *ARCH, *COMMON, *flags, "-c", src, "-o", obj]
+    cmd = [NVCC, *ARCH, *COMMON, *flags, *EXTRA, "-c", src, "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), flush=True)

@@ -222,105 +222,6 @@ k_energy3d(const __grid_constant__ K3Params P)
         const int w0 = min(max(i0 - 1, 0), P.n0 - 3);
         const int pstart = max(0, w0 - 1);
 
-        // d/dz (along lanes) and d/dy (along rows) of a staged plane.  The EDGE = false flavours are
-        // the pure interior formula (no branches: the two columns of a thread interleave freely);
-        // EDGE = true adds the one-sided formulas at the global faces.
-        auto dZ = [&](const double* B, int idx, unsigned cf, auto edge_tag) -> double {
-            double d = cdivm<MODE>(B[idx + 1] - B[idx - 1], cz.h2, cz.rh2);
-            if (decltype(edge_tag)::value) {
-                if (cf & 2u) d = edge3(ec_s[12], B[idx], ec_s[13], B[idx + 1], ec_s[14], B[idx + 2]);
-                else if (cf & 4u) d = edge3(ec_s[15], B[idx - 2], ec_s[16], B[idx - 1], ec_s[17], B[idx]);
-            }
-            return d;
-        };
-        // jedge: 0 interior, 1 row j == 0, 2 row j == n1-1 (warp-uniform)
-        auto dY = [&](const double* B, int idx, int jedge, auto edge_tag) -> double {
-            if (decltype(edge_tag)::value) {
-                if (jedge == 1) return edge3(ec_s[6], B[idx], ec_s[7], B[idx + RK], ec_s[8], B[idx + 2 * RK]);
-                if (jedge == 2) return edge3(ec_s[9], B[idx - 2 * RK], ec_s[10], B[idx - RK], ec_s[11], B[idx]);
-            }
-            return cdivm<MODE>(B[idx + RK] - B[idx - RK], cy.h2, cy.rh2);
-        };
-
-        // ---- task P(p): phi(p) at the own columns, and the x-derivative it completes -----------------
-        // phi_x(p-1) = (phi(p) - phi(p-2)) / 2dx needs phi(p-2) of the own column only.
-        auto taskP = [&](int p, int s3 /* p mod 3 */, double xp, double xxp, auto edge_tag) {
-            constexpr bool EDGE = decltype(edge_tag)::value;
-            const int s3m1 = (s3 == 0) ? 2 : s3 - 1, s3m2 = (s3 == 2) ? 0 : s3 + 1;
-            double* const ph_p = phi_ring + s3 * PLANE;
-            const double* const ph_m1 = phi_ring + s3m1 * PLANE;               // plane p-1
-            const double* const ph_m2 = phi_ring + s3m2 * PLANE;               // plane p-2
-            double* const px_w = px_ring + ((p + 3) & 3) * PLANE;              // phi_x(p-1)
-            const bool do_px = (p - 2 >= pstart);                              // interior formula
-            const bool do_px0 = EDGE && (p == 2) && (pstart == 0);             // phi_x(0), one-sided
-#pragma unroll 1
-            for (int jr = ty; jr <= jr_hi; jr += NW) {        // rows jr == ty (mod NW), as in task O
-                if (jr < jr_lo) continue;
-                const int base = jr * RK + tx;
-                double f[2];
-                if (IWB_DBG & 2) { f[0] = xxp + zz0; f[1] = xxp + zz1; }
-                else if (DT == IWB_F64) {
-                    const double sxy = xxp + yy_s[jr];
-                    const double s[2] = {sxy + zz0, sxy + zz1};
-                    // the row through the origin (r == 0 at one lane) takes the reference flavour
-                    const bool origin_row = (p == P.i_zero) && (j0 - 2 + jr == P.j_zero);
-                    // (exotic grids / parameters fail the host's operand-range proof: reference flavour throughout)
-                    if (MODE == 0) phi_exact_f64<2, true>(s, xp, pc, f, origin_row || !pc.prechecked);
-                    else phi_fast_f64<2>(s, xp, pc, f, origin_row || !pc.prechecked);
-                } else {
-                    const float sxy = __fadd_rn((float)xxp, (float)yy_s[jr]);
-                    const float s[2] = {__fadd_rn(sxy, (float)zz0), __fadd_rn(sxy, (float)zz1)};
-                    const bool origin_row = (p == P.i_zero) && (j0 - 2 + jr == P.j_zero);
-                    phi_exact_f32ref<2, true>(s, (float)xp, pc, f, origin_row || !pc.prechecked);
-                }
-                ph_p[base] = f[0];
-                ph_p[base + 32] = f[1];
-                if (do_px) {
-                    px_w[base] = cdivm<MODE>(f[0] - ph_m2[base], cx.h2, cx.rh2);
-                    px_w[base + 32] = cdivm<MODE>(f[1] - ph_m2[base + 32], cx.h2, cx.rh2);
-                }
-                if (EDGE && do_px0) {
-                    px_ring[base] = edge3(ec_s[0], ph_m2[base], ec_s[1], ph_m1[base], ec_s[2], f[0]);
-                    px_ring[base + 32] = edge3(ec_s[0], ph_m2[base + 32], ec_s[1], ph_m1[base + 32], ec_s[2], f[1]);
-                }
-            }
-        };
-
-        // ---- phi_x(n0-1), one-sided, from the last three phi planes (own columns) -----------------------
-        auto taskP_last = [&]() {
-            const int p = P.n0 - 1;
-            const double* const ph_p = phi_ring + (p % 3) * PLANE;
-            const double* const ph_m1 = phi_ring + ((p + 2) % 3) * PLANE;
-            const double* const ph_m2 = phi_ring + ((p + 1) % 3) * PLANE;
-            double* const px_w = px_ring + (p % 4) * PLANE;
-#pragma unroll 1
-            for (int jr = ty; jr <= jr_hi; jr += NW) {
-                if (jr < jr_lo) continue;
-                const int base = jr * RK + tx;
-                px_w[base] = edge3(ec_s[3], ph_m2[base], ec_s[4], ph_m1[base], ec_s[5], ph_p[base]);
-                px_w[base + 32] = edge3(ec_s[3], ph_m2[base + 32], ec_s[4], ph_m1[base + 32], ec_s[5], ph_p[base + 32]);
-            }
-        };
-
-        // ---- task C(q): phi_y(q), phi_z(q) from the phi(q) plane (reads neighbours' columns) ------------
-        auto taskC = [&](int q, int s3 /* q mod 3 */, auto edge_tag) {
-            constexpr bool EDGE = decltype(edge_tag)::value;
-            const double* const ph = phi_ring + s3 * PLANE;
-            double* const py_w = py_buf + (q & 1) * PLANE;
-            double* const pz_w = pz_buf + (q & 1) * PLANE;
-#pragma unroll 1
-            for (int jr = py_lo + ty; jr <= py_hi; jr += NW) {
-                const int base = jr * RK + tx;
-                const int jedge = EDGE ? ((t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0)) : 0;
-                py_w[base] = dY(ph, base, jedge, edge_tag);
-                py_w[base + 32] = dY(ph, base + 32, jedge, edge_tag);
-                if (jr >= 2 && jr <= Tj + 1) {
-                    pz_w[base] = dZ(ph, base, cf0, edge_tag);
-                    pz_w[base + 32] = dZ(ph, base + 32, cf1, edge_tag);
-                }
-            }
-        };
-
         // ---- sums of one row's two points (reproduce_rodal_exact.py:57-61, 220-224) ---------------------
         // e is masked to +0.0 at the non-output columns (an AND with the column's all-ones / zero word), and the
         // accumulators are sum(e) and sum(|e|): E+ = (sum + sum|.|)/2, E- = (sum - sum|.|)/2, formed per thread at the
@@ -377,63 +278,26 @@ k_energy3d(const __grid_constant__ K3Params P)
             }
         };
 
-        // ---- task O(i): second derivatives, rho, sums at the output columns of plane i --------------------
-        auto taskO = [&](int i, double xxi, auto edge_tag) {
-            constexpr bool EDGE = decltype(edge_tag)::value;
-            const double* const px_i = px_ring + (i & 3) * PLANE;
-            const double* const px_p = px_ring + ((i + 1) & 3) * PLANE;   // phi_x(i+1)
-            const double* const px_m = px_ring + ((i + 3) & 3) * PLANE;   // phi_x(i-1)
-            const double* const px_m2 = px_ring + ((i + 2) & 3) * PLANE;  // phi_x(i-2) (last plane only)
-            const double* const py_r = py_buf + (i & 1) * PLANE;
-            const double* const pz_r = pz_buf + (i & 1) * PLANE;
-            const int iedge = EDGE ? ((i == 0) ? 1 : ((i == P.n0 - 1) ? 2 : 0)) : 0;
-#pragma unroll 1
-            for (int jr = ty; jr <= Tj + 1; jr += NW) {       // the thread that produced phi_x of a column consumes it
-                if (jr < 2) continue;
-                const int base = jr * RK + tx;
-                const int jedge = EDGE ? ((t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0)) : 0;
-                const double yyj = yy_s[jr];
-                double rho2[2];
-#pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const int idx = base + 32 * a;
-                    const unsigned cf = a ? cf1 : cf0;
-                    double pxx;
-                    if (EDGE && iedge == 1)        // phi_x(0), (1), (2)
-                        pxx = edge3(ec_s[0], px_i[idx], ec_s[1], px_p[idx], ec_s[2], px_m2[idx]);
-                    else if (EDGE && iedge == 2)   // phi_x(n0-3), (n0-2), (n0-1)
-                        pxx = edge3(ec_s[3], px_m2[idx], ec_s[4], px_m[idx], ec_s[5], px_i[idx]);
-                    else
-                        pxx = cdivm<MODE>(px_p[idx] - px_m[idx], cx.h2, cx.rh2);
-                    const double pxy = dY(px_i, idx, jedge, edge_tag);
-                    const double pxz = dZ(px_i, idx, cf, edge_tag);
-                    const double pyy = dY(py_r, idx, jedge, edge_tag);
-                    const double pyz = dZ(py_r, idx, cf, edge_tag);
-                    const double pzz = dZ(pz_r, idx, cf, edge_tag);
-                    // K_ij = -phi_ij: the sign cancels in K^2 and in K_ij K^ij (reproduce_rodal_exact.py:198-212)
-                    const double tr = (pxx + pyy) + pzz;
-                    const double diag = (pxx * pxx + pyy * pyy) + pzz * pzz;
-                    const double off = (pxy * pxy + pxz * pxz) + pyz * pyz;
-                    const double kk = fma(2.0, off, diag);     // 2.0*off is exact -> same rounding as diag + 2.0*off
-                    rho2[a] = cdivm<MODE>(tr * tr - kk, P.c16pi, P.rc16pi);
-                }
-                if (EMIT) {
-                    const long long j = j0 - 2 + jr, k = k0 - 2 + tx;
-                    double* dst = P.rho_out + ((long long)(i - P.i_begin) * P.n1 + j) * P.n2 + k;
-                    if (cf0 & 16u) dst[0] = rho2[0];
-                    if (cf1 & 16u) dst[32] = rho2[1];
-                }
-                const double e2[2] = {rho2[0] * P.dV, rho2[1] * P.dV};
-                tally2(e2, yyj, xxi);
-            }
+        // ---- one-sided value at a global face: ((a f0) + (b f1)) + (c f2) over three consecutive entries --------
+        // `addr` is the entry AT the face, STEP the byte distance to its neighbour along the axis; `hi` selects the
+        // far face (entries idx-2, idx-1, idx with a1 b1 c1) instead of the near one (idx, idx+1, idx+2 with a0 b0 c0).
+        auto edge_at = [&](unsigned addr, auto step_tag, bool hi, const double* ec /* a0 b0 c0 a1 b1 c1 */) -> double {
+            constexpr int STEP = decltype(step_tag)::value;
+            const unsigned b = hi ? addr - 2u * (unsigned)STEP : addr;
+            const double* c = hi ? ec + 3 : ec;
+            return edge3(c[0], lds_f64<0>(b), c[1], lds_f64<STEP>(b), c[2], lds_f64<2 * STEP>(b));
         };
+        using step_k = std::integral_constant<int, 8>;           // next column
+        using step_j = std::integral_constant<int, RK * 8>;      // next row
 
-        // ================= interior flavours of the tasks (no global face in reach) =========================
-        // Same arithmetic as taskO / taskC / taskP with EDGE = false, written against explicit shared-memory
-        // addresses: per row one base register per plane and immediates for the neighbours, all loads of a row
-        // issued before its arithmetic, stores last.  O(i) and C(q) share the row loop (they read and write
-        // disjoint planes), so the short dependent chains of C fill the gaps of O.
-        auto stepOC_fast = [&](bool doO, int i, double xxi, bool doC, int q, int s3q) {
+        // ================= the three tasks of a step ===========================================================
+        // Explicit shared-memory addresses: per row one base register per plane and immediates for the
+        // neighbours; all loads of a row are issued before its arithmetic, stores last.  Every lane evaluates
+        // the interior (central) formula; rows / columns / planes ON a global face then override the affected
+        // derivatives with the one-sided formulas (numpy.gradient, edge_order=2) -- blocks that interior tiles
+        // skip with one uniform branch.  O(i) and C(q) share the row loop (they read and write disjoint
+        // planes), so the short dependent chains of C fill the gaps of O.
+        auto stepOC = [&](bool doO, int i, double xxi, bool doC, int q, int s3q) {
             // CTA-uniform plane offsets of this step (kept: computed once per step, not once per row)
             const unsigned o_pxi = keep_u32(PXB + (unsigned)(i & 3) * PLB);
             const unsigned o_pxp = keep_u32(PXB + (unsigned)((i + 1) & 3) * PLB);      // phi_x(i+1)
@@ -442,9 +306,12 @@ k_energy3d(const __grid_constant__ K3Params P)
             const unsigned o_ph = keep_u32((unsigned)s3q * PLB);                       // phi(q)
             const unsigned o_w = keep_u32(PYB + (unsigned)(q & 1) * PLB);              // phi_y(q); phi_z(q) at + 2 PLB
             constexpr int R8 = RK * 8, ZB = 2 * (int)PLB;
+            const int iedge = (i == 0) ? 1 : ((i == P.n0 - 1) ? 2 : 0);
+            const bool o_face = tile_edge || (iedge != 0);
             unsigned A = a_row0, ya = yy_row0;
 #pragma unroll 1
             for (int jr = ty; jr < RJ; jr += NW, A += ROWB, ya += NW * 8) {
+                const int jedge = (t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0);
                 if (doO && jr >= 2 && jr <= Tj + 1) {
                     const unsigned Ai = A + o_pxi, Ap = A + o_pxp, Am = A + o_pxm, Ay = A + o_py;
                     // column a = this lane, column b = lane + 32 (256 bytes further)
@@ -461,22 +328,47 @@ k_energy3d(const __grid_constant__ K3Params P)
                     const double zkpa = lds_f64<ZB + 8>(Ay), zkma = lds_f64<ZB - 8>(Ay);
                     const double zkpb = lds_f64<ZB + 256 + 8>(Ay), zkmb = lds_f64<ZB + 256 - 8>(Ay);
                     const double yyj = lds_f64<0>(ya);
-                    const double dpx[2] = {xpa - xma, xpb - xmb}, dxy[2] = {xjpa - xjma, xjpb - xjmb};
-                    const double dxz[2] = {xkpa - xkma, xkpb - xkmb}, dyy[2] = {yjpa - yjma, yjpb - yjmb};
-                    const double dyz[2] = {ykpa - ykma, ykpb - ykmb}, dzz[2] = {zkpa - zkma, zkpb - zkmb};
+                    double pxx[2] = {cdivm<MODE>(xpa - xma, cx.h2, cx.rh2), cdivm<MODE>(xpb - xmb, cx.h2, cx.rh2)};
+                    double pxy[2] = {cdivm<MODE>(xjpa - xjma, cy.h2, cy.rh2), cdivm<MODE>(xjpb - xjmb, cy.h2, cy.rh2)};
+                    double pxz[2] = {cdivm<MODE>(xkpa - xkma, cz.h2, cz.rh2), cdivm<MODE>(xkpb - xkmb, cz.h2, cz.rh2)};
+                    double pyy[2] = {cdivm<MODE>(yjpa - yjma, cy.h2, cy.rh2), cdivm<MODE>(yjpb - yjmb, cy.h2, cy.rh2)};
+                    double pyz[2] = {cdivm<MODE>(ykpa - ykma, cz.h2, cz.rh2), cdivm<MODE>(ykpb - ykmb, cz.h2, cz.rh2)};
+                    double pzz[2] = {cdivm<MODE>(zkpa - zkma, cz.h2, cz.rh2), cdivm<MODE>(zkpb - zkmb, cz.h2, cz.rh2)};
+                    if (o_face) {
+                        if (iedge == 1) {            // phi_x(0), (1), (2)
+                            const unsigned A2 = A + PXB + (unsigned)((i + 2) & 3) * PLB;
+                            pxx[0] = edge3(ec_s[0], lds_f64<0>(Ai), ec_s[1], lds_f64<0>(Ap), ec_s[2], lds_f64<0>(A2));
+                            pxx[1] = edge3(ec_s[0], lds_f64<256>(Ai), ec_s[1], lds_f64<256>(Ap), ec_s[2], lds_f64<256>(A2));
+                        } else if (iedge == 2) {     // phi_x(n0-3), (n0-2), (n0-1)
+                            const unsigned A2 = A + PXB + (unsigned)((i + 2) & 3) * PLB;
+                            pxx[0] = edge3(ec_s[3], lds_f64<0>(A2), ec_s[4], lds_f64<0>(Am), ec_s[5], lds_f64<0>(Ai));
+                            pxx[1] = edge3(ec_s[3], lds_f64<256>(A2), ec_s[4], lds_f64<256>(Am), ec_s[5], lds_f64<256>(Ai));
+                        }
+                        if (jedge) {                 // row on the face j == 0 / j == n1-1 (warp-uniform)
+                            pxy[0] = edge_at(Ai, step_j{}, jedge == 2, ec_s + 6);
+                            pxy[1] = edge_at(Ai + 256u, step_j{}, jedge == 2, ec_s + 6);
+                            pyy[0] = edge_at(Ay, step_j{}, jedge == 2, ec_s + 6);
+                            pyy[1] = edge_at(Ay + 256u, step_j{}, jedge == 2, ec_s + 6);
+                        }
+                        if (cf0 & 6u) {              // column on the face k == 0 / k == n2-1 (single lanes)
+                            pxz[0] = edge_at(Ai, step_k{}, (cf0 & 4u) != 0, ec_s + 12);
+                            pyz[0] = edge_at(Ay, step_k{}, (cf0 & 4u) != 0, ec_s + 12);
+                            pzz[0] = edge_at(Ay + (unsigned)ZB, step_k{}, (cf0 & 4u) != 0, ec_s + 12);
+                        }
+                        if (cf1 & 6u) {
+                            pxz[1] = edge_at(Ai + 256u, step_k{}, (cf1 & 4u) != 0, ec_s + 12);
+                            pyz[1] = edge_at(Ay + 256u, step_k{}, (cf1 & 4u) != 0, ec_s + 12);
+                            pzz[1] = edge_at(Ay + (unsigned)ZB + 256u, step_k{}, (cf1 & 4u) != 0, ec_s + 12);
+                        }
+                    }
                     double rho2[2];
 #pragma unroll
                     for (int a = 0; a < 2; ++a) {
-                        const double pxx = cdivm<MODE>(dpx[a], cx.h2, cx.rh2);
-                        const double pxy = cdivm<MODE>(dxy[a], cy.h2, cy.rh2);
-                        const double pxz = cdivm<MODE>(dxz[a], cz.h2, cz.rh2);
-                        const double pyy = cdivm<MODE>(dyy[a], cy.h2, cy.rh2);
-                        const double pyz = cdivm<MODE>(dyz[a], cz.h2, cz.rh2);
-                        const double pzz = cdivm<MODE>(dzz[a], cz.h2, cz.rh2);
-                        const double tr = (pxx + pyy) + pzz;
-                        const double diag = (pxx * pxx + pyy * pyy) + pzz * pzz;
-                        const double off = (pxy * pxy + pxz * pxz) + pyz * pyz;
-                        const double kk = fma(2.0, off, diag);
+                        // K_ij = -phi_ij: the sign cancels in K^2 and in K_ij K^ij (reproduce_rodal_exact.py:198-212)
+                        const double tr = (pxx[a] + pyy[a]) + pzz[a];
+                        const double diag = (pxx[a] * pxx[a] + pyy[a] * pyy[a]) + pzz[a] * pzz[a];
+                        const double off = (pxy[a] * pxy[a] + pxz[a] * pxz[a]) + pyz[a] * pyz[a];
+                        const double kk = fma(2.0, off, diag);     // 2.0*off is exact -> same rounding as diag + 2.0*off
                         rho2[a] = cdivm<MODE>(tr * tr - kk, P.c16pi, P.rc16pi);
                     }
                     if (EMIT) {
@@ -495,10 +387,18 @@ k_energy3d(const __grid_constant__ K3Params P)
                     const double hjpb = lds_f64<256 + R8>(Ah), hjmb = lds_f64<256 - R8>(Ah);
                     const double hkpa = lds_f64<8>(Ah), hkma = lds_f64<-8>(Ah);
                     const double hkpb = lds_f64<256 + 8>(Ah), hkmb = lds_f64<256 - 8>(Ah);
-                    const double pya = cdivm<MODE>(hjpa - hjma, cy.h2, cy.rh2);
-                    const double pyb = cdivm<MODE>(hjpb - hjmb, cy.h2, cy.rh2);
-                    const double pza = cdivm<MODE>(hkpa - hkma, cz.h2, cz.rh2);
-                    const double pzb = cdivm<MODE>(hkpb - hkmb, cz.h2, cz.rh2);
+                    double pya = cdivm<MODE>(hjpa - hjma, cy.h2, cy.rh2);
+                    double pyb = cdivm<MODE>(hjpb - hjmb, cy.h2, cy.rh2);
+                    double pza = cdivm<MODE>(hkpa - hkma, cz.h2, cz.rh2);
+                    double pzb = cdivm<MODE>(hkpb - hkmb, cz.h2, cz.rh2);
+                    if (tile_edge) {
+                        if (jedge) {
+                            pya = edge_at(Ah, step_j{}, jedge == 2, ec_s + 6);
+                            pyb = edge_at(Ah + 256u, step_j{}, jedge == 2, ec_s + 6);
+                        }
+                        if (cf0 & 6u) pza = edge_at(Ah, step_k{}, (cf0 & 4u) != 0, ec_s + 12);
+                        if (cf1 & 6u) pzb = edge_at(Ah + 256u, step_k{}, (cf1 & 4u) != 0, ec_s + 12);
+                    }
                     sts_f64<0>(Aw, pya);
                     sts_f64<256>(Aw, pyb);
                     if (z_row) {
@@ -509,13 +409,15 @@ k_energy3d(const __grid_constant__ K3Params P)
             }
         };
 
-        // P(p) for an interior tile: phi(p) at the own columns and phi_x(p-1) = (phi(p) - phi(p-2)) / 2dx
-        auto taskP_fast = [&](int p, int s3 /* p mod 3 */, double xp, double xxp) {
+        // P(p): phi(p) at the own columns and phi_x(p-1) = (phi(p) - phi(p-2)) / 2dx, which needs phi(p-2) of the
+        // own column only; with p == 2 at the start of the axis also the one-sided phi_x(0).
+        auto taskP = [&](int p, int s3 /* p mod 3 */, double xp, double xxp) {
             const int s3m2 = (s3 == 2) ? 0 : s3 + 1;
             const unsigned o_p = keep_u32((unsigned)s3 * PLB);                         // phi(p)
             const unsigned o_m2 = keep_u32((unsigned)s3m2 * PLB);                      // phi(p-2)
             const unsigned o_xw = keep_u32(PXB + (unsigned)((p + 3) & 3) * PLB);       // phi_x(p-1)
             const bool do_px = (p - 2 >= pstart);
+            const bool do_px0 = (p == 2) && (pstart == 0);                             // phi_x(0), one-sided
             unsigned A = a_row0, ya = yy_row0;
 #pragma unroll 1
             for (int jr = ty; jr <= jr_hi; jr += NW, A += ROWB, ya += NW * 8) {
@@ -528,7 +430,9 @@ k_energy3d(const __grid_constant__ K3Params P)
                 else if (DT == IWB_F64) {
                     const double sxy = xxp + yyj;
                     const double s[2] = {sxy + zz0, sxy + zz1};
+                    // the row through the origin (r == 0 at one lane) takes the reference flavour
                     const bool origin_row = (p == P.i_zero) && (j0 - 2 + jr == P.j_zero);
+                    // (exotic grids / parameters fail the host's operand-range proof: reference flavour throughout)
                     if (MODE == 0) phi_exact_f64<2, true>(s, xp, pc, f, origin_row || !pc.prechecked);
                     else phi_fast_f64<2>(s, xp, pc, f, origin_row || !pc.prechecked);
                 } else {
@@ -545,6 +449,28 @@ k_energy3d(const __grid_constant__ K3Params P)
                     sts_f64<0>(Ax, cdivm<MODE>(f[0] - m2a, cx.h2, cx.rh2));
                     sts_f64<256>(Ax, cdivm<MODE>(f[1] - m2b, cx.h2, cx.rh2));
                 }
+                if (do_px0) {      // p == 2: phi(0) is plane p-2 (slot 0), phi(1) in slot 1; phi_x(0) goes to slot 0 of its ring
+                    const unsigned A1 = A + PLB, Ax0 = A + PXB;
+                    sts_f64<0>(Ax0, edge3(ec_s[0], m2a, ec_s[1], lds_f64<0>(A1), ec_s[2], f[0]));
+                    sts_f64<256>(Ax0, edge3(ec_s[0], m2b, ec_s[1], lds_f64<256>(A1), ec_s[2], f[1]));
+                }
+            }
+        };
+
+
+        // ---- phi_x(n0-1), one-sided, from the last three phi planes (own columns) -----------------------
+        auto taskP_last = [&]() {
+            const int p = P.n0 - 1;
+            const double* const ph_p = phi_ring + (p % 3) * PLANE;
+            const double* const ph_m1 = phi_ring + ((p + 2) % 3) * PLANE;
+            const double* const ph_m2 = phi_ring + ((p + 1) % 3) * PLANE;
+            double* const px_w = px_ring + (p % 4) * PLANE;
+#pragma unroll 1
+            for (int jr = ty; jr <= jr_hi; jr += NW) {
+                if (jr < jr_lo) continue;
+                const int base = jr * RK + tx;
+                px_w[base] = edge3(ec_s[3], ph_m2[base], ec_s[4], ph_m1[base], ec_s[5], ph_p[base]);
+                px_w[base + 32] = edge3(ec_s[3], ph_m2[base + 32], ec_s[4], ph_m1[base + 32], ec_s[5], ph_p[base + 32]);
             }
         };
 
@@ -612,27 +538,10 @@ k_energy3d(const __grid_constant__ K3Params P)
             for (int s = 0; s < NSHA; ++s) { sh_sum[s] = 0.0; sh_abs[s] = 0.0; sh_cnt[s] = 0; }
         };
 
-        auto runP = [&](int p, int s3, double xp, double xxp) {
-            if (tile_edge || (p == 2 && pstart == 0)) taskP(p, s3, xp, xxp, std::true_type{});
-            else taskP_fast(p, s3, xp, xxp);
-        };
-        auto runC = [&](int q, int s3) {
-            if (tile_edge) taskC(q, s3, std::true_type{});
-            else stepOC_fast(false, 0, 0.0, true, q, s3);
-        };
+        auto runP = [&](int p, int s3, double xp, double xxp) { taskP(p, s3, xp, xxp); };
+        auto runC = [&](int q, int s3) { stepOC(false, 0, 0.0, true, q, s3); };
         // O(i) followed by C(i+1) (the latter when doC)
-        auto runOC = [&](int i, double xxi, bool doC, int m3p1) {
-            const bool doO = !(IWB_DBG & 1);
-            if (tile_edge) {
-                if (doO) taskO(i, xxi, std::true_type{});
-                if (doC) taskC(i + 1, m3p1, std::true_type{});
-            } else if (i == 0 || i == P.n0 - 1) {       // interior tile, one-sided plane of axis 0
-                if (doO) taskO(i, xxi, std::true_type{});
-                if (doC) stepOC_fast(false, 0, 0.0, true, i + 1, m3p1);
-            } else {
-                stepOC_fast(doO, i, xxi, doC, i + 1, m3p1);
-            }
-        };
+        auto runOC = [&](int i, double xxi, bool doC, int m3p1) { stepOC(!(IWB_DBG & 1), i, xxi, doC, i + 1, m3p1); };
         // phi_x(n0-1) may be written once every phi plane exists and its ring slot (that of phi_x(n0-5),
         // last read by O(n0-4)) is dead, i.e. from the step of output plane n0-3 on; it is first needed
         // by O(n0-2) (n0 == 3: by every plane, and 0 >= n0-3 holds).
