@@ -8,6 +8,7 @@
 
 #include <chrono>
 #include <string>
+#include <vector>
 
 #include "energy3d_launch.cuh"
 #include "radial_profile.cuh"
@@ -53,6 +54,34 @@ struct Launch3 {
     bool emit;
 };
 
+// Span boundaries over `units` work units for `ctas` persistent CTAs: `static_pct` % of the units in one equal span
+// per CTA (taken first, in index order), the rest in spans of geometrically decreasing size (guided self-scheduling,
+// half of what an even split of the remainder would give, down to one unit) that level out the cost differences
+// between tiles.  Every span boundary is a prologue of the kernel, so few and large spans are cheap; the last spans
+// bound the scheduling tail, so they are single units.
+static std::vector<int> make_spans(long long units, int ctas, int static_pct)
+{
+    std::vector<int> b;
+    b.push_back(0);
+    if (ctas < 1) ctas = 1;
+    long long u = 0;
+    if (units >= 4LL * ctas && static_pct > 0) {
+        const long long us = units * static_pct / 100;
+        for (int s = 1; s <= ctas; ++s) {
+            const long long e = us * s / ctas;
+            if (e > u) { b.push_back((int)e); u = e; }
+        }
+    }
+    while (u < units) {
+        long long c = (units - u + 2LL * ctas - 1) / (2LL * ctas);
+        if (c < 1) c = 1;
+        u += c;
+        if (u > units) u = units;
+        b.push_back((int)u);
+    }
+    return b;
+}
+
 // Stages coordinates into `hc` (pinned) -> `dc` (device) on `st` and fills the launch record.
 static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, DevBuf& coords, DevBuf& partial,
                         DevBuf& counter, cudaStream_t st, double* rho_dev, Launch3* L)
@@ -61,10 +90,15 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
     const int cfg_id = config_is_built(h->k3_config, p->dtype, p->nshell, rho_dev != nullptr) ? h->k3_config : 0;
     const K3Config cfg = kConfigs[cfg_id];
 
+    // work spans of the fused kernel (see k_energy3d), staged behind the coordinates
+    const int ntj_ = (n1 + (cfg.rj - 4) - 1) / (cfg.rj - 4), ntk_ = (n2 + TK_MAX - 1) / TK_MAX;
+    const std::vector<int> spans = make_spans((long long)ntj_ * ntk_ * ((p->i_end - p->i_begin + FLUSH - 1) / FLUSH),
+                                              h->sm_count, h->k3_static_pct);
     // coordinates: x, x*x, y*y, z*z (squares rounded once in the coordinate dtype, as x*x is in NumPy)
     const size_t ncoord = (size_t)2 * n0 + n1 + n2;
-    IWB_CUDA(h_coords.reserve(ncoord * sizeof(double)));
-    IWB_CUDA(coords.reserve(ncoord * sizeof(double)));
+    const size_t stage_bytes = ncoord * sizeof(double) + spans.size() * sizeof(int);
+    IWB_CUDA(h_coords.reserve(stage_bytes));
+    IWB_CUDA(coords.reserve(stage_bytes));
     double* hc = (double*)h_coords.p;
     double *hx = hc, *hxx = hc + n0, *hyy = hc + 2 * n0, *hzz = hc + 2 * n0 + n1;
     if (p->dtype == IWB_F64) {
@@ -76,7 +110,8 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
         for (int j = 0; j < n1; ++j) { float f = (float)p->y[j]; hyy[j] = (double)(f * f); }
         for (int k = 0; k < n2; ++k) { float f = (float)p->z[k]; hzz[k] = (double)(f * f); }
     }
-    IWB_CUDA(cudaMemcpyAsync(coords.p, hc, ncoord * sizeof(double), cudaMemcpyHostToDevice, st));
+    memcpy(hc + ncoord, spans.data(), spans.size() * sizeof(int));
+    IWB_CUDA(cudaMemcpyAsync(coords.p, hc, stage_bytes, cudaMemcpyHostToDevice, st));
 
     K3Params& P = L->P;
     memset(&P, 0, sizeof(P));
@@ -86,23 +121,11 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
     P.ntk = (n2 + TK_MAX - 1) / TK_MAX;
     const int ntiles = P.ntj * P.ntk;
     const int planes = p->i_end - p->i_begin;
-    // planes per work item: each item pays a 4-plane phi prologue, so items are as long as the dynamic
-    // schedule allows: <= 128 planes, halved while there are fewer than 12 items per SM, >= 32 planes
-    // (a single flush block only when even that cannot fill the GPU)
-    int seg_len = ((planes + FLUSH - 1) / FLUSH) * FLUSH;
-    if (h->k3_seg_len > 0) {
-        seg_len = ((h->k3_seg_len + FLUSH - 1) / FLUSH) * FLUSH;
-    } else {
-        if (seg_len > 8 * FLUSH) seg_len = 8 * FLUSH;
-        const long long want = 12LL * h->sm_count;
-        while (seg_len > 2 * FLUSH && (long long)ntiles * ((planes + seg_len - 1) / seg_len) < want)
-            seg_len = ((seg_len / 2 + FLUSH - 1) / FLUSH) * FLUSH;
-        if ((long long)ntiles * ((planes + seg_len - 1) / seg_len) < h->sm_count && seg_len > FLUSH) seg_len = FLUSH;
-    }
-    P.seg_len = seg_len;
-    P.nseg = (planes + seg_len - 1) / seg_len;
-    P.nitems = P.nseg * ntiles;
+    const int nfb_slab = (planes + FLUSH - 1) / FLUSH;
+    P.nfb_slab = nfb_slab;
     double* dc = (double*)coords.p;
+    P.span_begin = (const int*)(dc + ncoord);
+    P.nspans = (int)spans.size() - 1;
     P.x = dc; P.xx = dc + n0; P.yy = dc + 2 * n0; P.zz = dc + 2 * n0 + n1;
     P.pc = make_phi_const(p->rho, p->sigma, p->v, p->eps, p->sinh_rs, p->cosh_rs);
     {
@@ -145,7 +168,7 @@ static int launch_slab(iwb_handle* h, const Launch3& L, double* table, cudaStrea
 {
     cudaError_t e = launch_k3(L.dtype, L.mode, L.nshell, L.emit, L.cfg_id, L.P, h->sm_count, st);
     if (e != cudaSuccess) return fail(IWB_ERR_CUDA, std::string("k_energy3d launch: ") + cudaGetErrorString(e));
-    k_reduce_tiles<<<L.fb1 - L.fb0, 128, 0, st>>>(L.P.partial, table, L.fb0, L.ntiles, L.P.counter);
+    k_reduce_tiles<<<L.fb1 - L.fb0, 512, 0, st>>>(L.P.partial, table, L.fb0, L.ntiles, L.P.counter);
     IWB_CUDA(cudaGetLastError());
     return IWB_OK;
 }

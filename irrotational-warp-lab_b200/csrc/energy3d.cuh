@@ -60,8 +60,10 @@ constexpr int NEDGE = 18;           // one-sided coefficients a0 b0 c0 a1 b1 c1 
 struct K3Params {
     int n0, n1, n2;
     int i_begin, i_end;            // planes to evaluate (global indices)
-    int seg_len;                   // planes per work item (multiple of FLUSH)
-    int nseg, ntj, ntk, nitems;
+    int ntj, ntk;                  // tiles of the (j, k) plane
+    int nfb_slab;                  // flush blocks (FLUSH planes each) in [i_begin, i_end)
+    int nspans;                    // work spans, handed out dynamically in index order
+    const int* span_begin;         // [nspans + 1] unit boundaries; unit u = tile rank * nfb_slab + flush block
     const double* x;               // [n0]  (float32 values widened for the f32ref path)
     const double* xx;              // [n0]  x*x   (rounded in the path's coordinate dtype)
     const double* yy;              // [n1]  y*y
@@ -147,21 +149,31 @@ k_energy3d(const __grid_constant__ K3Params P)
         }
         mbar_parity ^= 1u;
     };
+    // Work distribution.  A unit is (tile, flush block); units are ordered tile-major, and a SPAN is a contiguous range
+    // of units.  A CTA marches through the units of a span without interruption -- the rings stay primed, so only the
+    // first unit of a tile within a span pays the 4-plane phi prologue -- and spans are handed out in index order by an
+    // atomic counter: one large span per CTA first (70 % of the work, no scheduling tail inside it), then ever
+    // smaller ones that even out the differences (host: make_spans).  Partial sums go to fixed slots, so the result
+    // does not depend on which CTA ran which span.
     for (;;) {
-        // dynamic schedule: items are handed out in index order; their partial sums go to fixed slots,
-        // so the result does not depend on which CTA ran which item
-        __syncthreads();                 // previous item's shared memory (and s_item) is dead
-        if (threadIdx.x == 0) s_item = (int)atomicAdd(P.counter, 1u);
-        __syncthreads();
-        const int item = s_item;
-        if (item >= P.nitems) break;
-        const int seg = item / ntiles;
-        // Tiles that touch a global face cost ~1.3x an interior tile (one-sided formulas, divergent lanes), so each
-        // segment hands them out first: longest-processing-time-first keeps the tail of the dynamic schedule short.
+    __syncthreads();                     // s_item of the previous span is dead
+    if (threadIdx.x == 0) s_item = (int)atomicAdd(P.counter, 1u);
+    __syncthreads();
+    const int span = s_item;
+    if (span >= P.nspans) break;
+    int unit = P.span_begin[span];
+    const int unit_end = P.span_begin[span + 1];
+    while (unit < unit_end) {
+        __syncthreads();                 // previous item's shared memory is dead
+        const int rnk = unit / P.nfb_slab;
+        const int fblk0 = unit - rnk * P.nfb_slab;
+        const int fblk1 = min(P.nfb_slab, fblk0 + (unit_end - unit));
+        unit += fblk1 - fblk0;
+        // Tiles that touch a global face cost more than interior tiles (one-sided formulas, divergent lanes); they come
+        // first in the unit order, i.e. in the large spans.
         // rank -> tile: row tj = 0, row tj = ntj-1, the two edge columns of the rows between, then the interior.
         int tile;
         {
-            const int rnk = item - seg * ntiles;
             if (P.ntj <= 2 || P.ntk <= 2) tile = rnk;
             else if (rnk < P.ntk) tile = rnk;
             else if (rnk < 2 * P.ntk) tile = (P.ntj - 1) * P.ntk + (rnk - P.ntk);
@@ -177,8 +189,8 @@ k_energy3d(const __grid_constant__ K3Params P)
         const int tj = tile / P.ntk, tk = tile - tj * P.ntk;
         const int j0 = tile_begin(tj, P.ntj, P.n1), Tj = tile_begin(tj + 1, P.ntj, P.n1) - j0;
         const int k0 = tile_begin(tk, P.ntk, P.n2), Tk = tile_begin(tk + 1, P.ntk, P.n2) - k0;
-        const int i0 = P.i_begin + seg * P.seg_len;
-        const int i1 = min(P.i_end, i0 + P.seg_len);
+        const int i0 = P.i_begin + fblk0 * FLUSH;
+        const int i1 = min(P.i_end, P.i_begin + fblk1 * FLUSH);
 
         // region rows [jr_lo, jr_hi] exist in the grid; j == 0 is region row 2 of a low-edge tile,
         // j == n1-1 is region row Tj+1 of a high-edge tile
@@ -629,37 +641,52 @@ k_energy3d(const __grid_constant__ K3Params P)
             if (((i + 1) & (FLUSH - 1)) == 0 || i == i1 - 1) flush(i / FLUSH, i);
             m3 = m3p1;
         }
-    }
+    }   // units of the span
+    }   // spans
 }
 
 // ---- fixed-order sum over tiles: partial[fb][tile][ROW] -> table[fb][ROW] ----------------------
 // (static: every translation unit that includes this header gets its own copy)
-static __global__ void __launch_bounds__(128) k_reduce_tiles(const double* __restrict__ partial,
-                                                             double* __restrict__ table, int fb_begin, int ntiles,
-                                                             unsigned int* counter = nullptr)
+// One block per flush block, blockDim.x = 32 * NCH threads (NCH a power of two <= 32): thread (slot q, chain c) adds the
+// tiles t = c, c + NCH, c + 2 NCH, ... in increasing order, then the chains are combined by a fixed binary tree in
+// shared memory.  Deterministic and independent of the slab decomposition (a flush block always sees the same tiles).
+// With 16 chains the 522 tiles of n = 1024 are 33 dependent additions per thread instead of 131.
+static_assert(ROW <= 32, "one slot per lane");
+static __global__ void __launch_bounds__(1024) k_reduce_tiles(const double* __restrict__ partial,
+                                                              double* __restrict__ table, int fb_begin, int ntiles,
+                                                              unsigned int* counter = nullptr)
 {
+    __shared__ double s_part[32][33];
     if (counter && blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;    // re-arm the work queue of k_energy3d
     const int fb = fb_begin + blockIdx.x;
-    const int q = threadIdx.x;            // one thread per row slot
-    if (q >= ROW) return;
+    const int q = threadIdx.x & 31, c = threadIdx.x >> 5, nch = blockDim.x >> 5;
     const bool is_int = (q >= 2 && q < 6) || (q >= 6 + 2 * IWB_MAX_SHELLS);
-    const double* src = partial + (size_t)fb * ntiles * ROW + q;
-    // 4 interleaved chains (tile t goes to chain t mod 4), then a fixed combine: deterministic
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    long long i0 = 0, i1 = 0, i2 = 0, i3 = 0;
-    int t = 0;
-    for (; t + 4 <= ntiles; t += 4) {
-        const double v0 = src[(size_t)(t + 0) * ROW], v1 = src[(size_t)(t + 1) * ROW];
-        const double v2 = src[(size_t)(t + 2) * ROW], v3 = src[(size_t)(t + 3) * ROW];
-        if (is_int) {
-            i0 += __double_as_longlong(v0); i1 += __double_as_longlong(v1);
-            i2 += __double_as_longlong(v2); i3 += __double_as_longlong(v3);
-        } else { a0 += v0; a1 += v1; a2 += v2; a3 += v3; }
+    double a = 0.0;
+    long long ia = 0;
+    if (q < ROW) {
+        const double* src = partial + (size_t)fb * ntiles * ROW + q;
+        int t = c;
+        for (; t + 3 * nch < ntiles; t += 4 * nch) {      // four loads in flight, added in tile order
+            const double v0 = src[(size_t)t * ROW], v1 = src[(size_t)(t + nch) * ROW];
+            const double v2 = src[(size_t)(t + 2 * nch) * ROW], v3 = src[(size_t)(t + 3 * nch) * ROW];
+            if (is_int) ia += __double_as_longlong(v0) + __double_as_longlong(v1) + __double_as_longlong(v2) + __double_as_longlong(v3);
+            else { a += v0; a += v1; a += v2; a += v3; }
+        }
+        for (; t < ntiles; t += nch) {
+            const double v = src[(size_t)t * ROW];
+            if (is_int) ia += __double_as_longlong(v); else a += v;
+        }
     }
-    if (t < ntiles) { const double v = src[(size_t)t * ROW]; if (is_int) i0 += __double_as_longlong(v); else a0 += v; ++t; }
-    if (t < ntiles) { const double v = src[(size_t)t * ROW]; if (is_int) i1 += __double_as_longlong(v); else a1 += v; ++t; }
-    if (t < ntiles) { const double v = src[(size_t)t * ROW]; if (is_int) i2 += __double_as_longlong(v); else a2 += v; ++t; }
-    table[(size_t)fb * ROW + q] = is_int ? __longlong_as_double((i0 + i1) + (i2 + i3)) : ((a0 + a1) + (a2 + a3));
+    s_part[c][q] = is_int ? __longlong_as_double(ia) : a;
+    __syncthreads();
+    for (int h = nch >> 1; h > 0; h >>= 1) {
+        if (c < h) {
+            const double lo = s_part[c][q], hi = s_part[c + h][q];
+            s_part[c][q] = is_int ? __longlong_as_double(__double_as_longlong(lo) + __double_as_longlong(hi)) : lo + hi;
+        }
+        __syncthreads();
+    }
+    if (c == 0 && q < ROW) table[(size_t)fb * ROW + q] = s_part[0][q];
 }
 
 // ---- fixed-order sum over flush blocks: table[nrows][ROW] -> out[ROW] ------------------------------

@@ -26,7 +26,7 @@ static cudaError_t launch_one(const K3Params& P, int sm_count, cudaStream_t st)
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     int grid = sm_count * per_sm;
-    if (grid > P.nitems) grid = P.nitems;
+    if (grid > P.nspans) grid = P.nspans;
     kern<<<grid, NW * 32, smem, st>>>(P);
     return cudaGetLastError();
 }

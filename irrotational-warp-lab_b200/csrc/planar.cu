@@ -389,7 +389,7 @@ int iwb_energy_axisym(iwb_handle* h, const iwb_params_axisym* p, iwb_result* out
         else launch_axisym<IWB_F32_REF, false>(p->nshell, P, ntiles, c.stream);
     }
     IWB_CUDA(cudaGetLastError());
-    k_reduce_tiles<<<1, 128, 0, c.stream>>>(P.partial, (double*)c.out.p, 0, ntiles);
+    k_reduce_tiles<<<1, 1024, 0, c.stream>>>(P.partial, (double*)c.out.p, 0, ntiles);
     IWB_CUDA(cudaGetLastError());
     IWB_CUDA(cudaMemcpyAsync(c.h_out.p, c.out.p, ROW_BYTES_MIN, cudaMemcpyDeviceToHost, c.stream));
     IWB_CUDA(cudaEventRecord(c.ev1, c.stream));
@@ -447,7 +447,7 @@ int iwb_slice_z0(iwb_handle* h, const iwb_params_slice* p, iwb_slice_result* out
     k_slice_phi<<<grid, 256, 0, c.stream>>>(P);
     k_slice_beta<<<grid, 256, 0, c.stream>>>(P);
     k_slice_rho<<<grid, 256, 0, c.stream>>>(P);
-    k_reduce_tiles<<<1, 128, 0, c.stream>>>(P.partial, (double*)c.out.p, 0, nblocks);
+    k_reduce_tiles<<<1, 1024, 0, c.stream>>>(P.partial, (double*)c.out.p, 0, nblocks);
     IWB_CUDA(cudaGetLastError());
     IWB_CUDA(cudaMemcpyAsync(c.h_out.p, c.out.p, ROW_BYTES_MIN, cudaMemcpyDeviceToHost, c.stream));
     IWB_CUDA(cudaEventRecord(c.ev1, c.stream));
