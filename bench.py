@@ -5,10 +5,11 @@
 
 One *step* = one full evaluation of the hot path on the synthetic (analytic) grid rho=5 sigma=4
 v=1 extent=66, shells r<=40 / r<=60: fused kernel -> fixed-order tile reduction -> (N>1: NCCL
-all-gather of the 15 KB partial table) -> fixed-order row reduction -> 240-byte result to the host.
+all-gather of the 245 KB chain sums) -> fixed-order row reduction -> 240-byte result to the host.
 
-N = 1 runs in this process; N > 1 is launched by torchrun, one rank per GPU, each rank owning one
-slab of axis 0 (weak scaling is NOT used: the volume is fixed, so "scaling": "strong").
+N = 1 runs in this process; N > 1 is launched by torchrun, one rank per GPU, each rank owning an
+interleaved shard of the (j, k) tiles along the whole of axis 0 (weak scaling is NOT used: the volume
+is fixed, so "scaling": "strong").
 
 Printed JSON (one line, rank 0):
   value   : Gpoints/s, whole job, inputs (coordinates) resident in HBM -- CUDA events on the
@@ -158,7 +159,7 @@ def main(argv=None):
     import torch.distributed as dist
 
     from irrotational_warp_lab_b200 import backend, distributed, sharding
-    from irrotational_warp_lab_b200._capi import ROW_WIDTH
+    from irrotational_warp_lab_b200._capi import ROW_WIDTH, TILE_CHAINS
     from irrotational_warp_lab_b200.engine import get_engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -178,7 +179,10 @@ def main(argv=None):
     eng = get_engine(local_rank)
     x = np.linspace(-EXTENT, EXTENT, n)
     dx = float(x[1] - x[0])
-    i_begin, i_end = sharding.slab_bounds(n, world)[rank]
+    # N > 1: interleaved tile shards (every rank marches its tiles along the whole of axis 0); the slab decomposition
+    # is the fall-back for a world size that does not divide the 16 tile chains
+    tiles = sharding.tile_shard(world, rank) if world > 1 else None
+    i_begin, i_end = (0, n) if (world == 1 or tiles is not None) else sharding.slab_bounds(n, world)[rank]
     nfb = sharding.num_flush_blocks(n)
     r0, r1 = sharding.rows_of_slab(i_begin, i_end)
 
@@ -188,15 +192,22 @@ def main(argv=None):
         torch.cuda.synchronize(dev)
 
     # ---------------- value: coordinates resident on the device, CUDA events ----------------------------
+    shard_kw = dict(tile_stride=tiles[0], tile_first=tiles[1]) if tiles is not None else {}
     plan = eng.plan3d(x=x, y=x, z=x, dx=dx, dy=dx, dz=dx, rho=RHO, sigma=SIGMA, v=V, dtype="float64", shells=SHELLS,
-                      i_begin=i_begin, i_end=i_end) if i_end > i_begin else None
-    table = torch.zeros((nfb, ROW_WIDTH), dtype=torch.float64, device=dev)
+                      i_begin=i_begin, i_end=i_end, **shard_kw) if i_end > i_begin else None
+    if tiles is not None:
+        table = torch.zeros((nfb, TILE_CHAINS // world, ROW_WIDTH), dtype=torch.float64, device=dev)     # chain sums
+    else:
+        table = torch.zeros((nfb, ROW_WIDTH), dtype=torch.float64, device=dev)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
 
     def resident_step():
         if plan is not None:
             plan.run_async(table.data_ptr(), stream.cuda_stream)
+        if tiles is not None:
+            full = sharding.all_gather_chains(table, world)
+            return eng.reduce_chains(full.data_ptr(), world, nfb, len(SHELLS), stream.cuda_stream)
         full = sharding.all_gather_table(table[r0:r1], n, world) if world > 1 else table
         return eng.reduce_table(full.data_ptr(), nfb, len(SHELLS), stream.cuda_stream)
 
@@ -222,7 +233,8 @@ def main(argv=None):
         dev_ms = float(t.item())
     ms_per_step = dev_ms / steps
     value = n ** 3 / (ms_per_step * 1e-3) / 1e9
-    launches_value = steps * ((2 if plan is not None else 0) + 1)      # k_energy3d, k_reduce_tiles, k_reduce_rows
+    # k_energy3d, k_reduce_tiles | k_chain_sums, (k_combine_chains,) k_reduce_rows
+    launches_value = steps * ((2 if plan is not None else 0) + (2 if tiles is not None else 1))
 
     # kernel-only duration of the dominant kernel (rank 0's slab), CUDA events on its launching stream
     kern_ms = []
@@ -256,7 +268,7 @@ def main(argv=None):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = n ** 3 * steps / e2e_s / 1e9
-    launches_e2e = steps * 3
+    launches_e2e = steps * (4 if tiles is not None else 3)
     if rank == 0:
         sampler.stop()
     clocks = sampler.summary(t_region0, time.perf_counter()) if rank == 0 else None
@@ -268,7 +280,8 @@ def main(argv=None):
 
     if rank == 0:
         peak = eng.measure_fma_peak(False)
-        pts_per_s_kernel = (i_end - i_begin) * n * n / (kern_ms_avg * 1e-3) if kern_ms_avg else 0.0
+        kernel_points = (i_end - i_begin) * n * n // (world if tiles is not None else 1)     # this rank's share
+        pts_per_s_kernel = kernel_points / (kern_ms_avg * 1e-3) if kern_ms_avg else 0.0
         achieved_contract = pts_per_s_kernel * SLOTS_CONTRACT * 2 / 1e12
         achieved_exact = pts_per_s_kernel * SLOTS_EXACT_ALG * 2 / 1e12
         peaks_file = {}
@@ -280,15 +293,17 @@ def main(argv=None):
         # coordinates in; per-(flush block, tile) partial rows out (36 x 60 tiles of the default 40 x 64 geometry);
         # they are consumed by k_reduce_tiles and usually never leave L2
         ntiles = -(-n // 36) * -(-n // 60)
-        alg_bytes = 8.0 * (2 * n + n + n) + 8.0 * ROW_WIDTH * (r1 - r0) * ntiles
+        alg_bytes = 8.0 * (2 * n + n + n) + 8.0 * ROW_WIDTH * (r1 - r0) * ntiles / (world if tiles is not None else 1)
         line = {
             "metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"3D n={n}^3 fp64 energy-condition evaluation (BASELINE config 4): rho=5 sigma=4 v=1 "
                                    f"extent=66, shells r<=40 and r<=60, exact (IEEE-replay) mode",
-                       "sharding": f"{world} slab(s) of axis 0, analytic halo recompute, all-gather of a "
-                                   f"{nfb}x{ROW_WIDTH} f64 table" if world > 1 else "single GPU",
+                       "sharding": ("single GPU" if world == 1 else
+                                    f"{world} interleaved tile shards (every {world}-th 36x60 tile of the (j,k) plane, whole axis 0), "
+                                    f"all-gather of {nfb}x{TILE_CHAINS}x{ROW_WIDTH} f64 chain sums" if tiles is not None else
+                                    f"{world} slab(s) of axis 0, analytic halo recompute, all-gather of a {nfb}x{ROW_WIDTH} f64 table"),
                        "l2": "256 MiB buffer written between timed steps (inputs are 32 KB of coordinates)",
                        "timing": "per-step CUDA-event pairs on the launching stream, summed; max over ranks"},
             "e2e": {"value": e2e_value, "unit": "Gpoints/s", "h2d_bytes_per_step": 8 * 4 * n,
@@ -303,7 +318,7 @@ def main(argv=None):
                 "note": "FP64-pipe bound: achieved = kernel points/s x 114 FP64 issue slots/point x 2 (slots of the "
                         "bit-exact algorithm, counted from SASS, DESIGN.md §6); peak = register-resident DFMA "
                         "microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 vector figure)",
-                "kernel_ms": kern_ms_avg, "kernel_points": (i_end - i_begin) * n * n,
+                "kernel_ms": kern_ms_avg, "kernel_points": kernel_points,
                 "contract": {"slots_per_point": SLOTS_CONTRACT, "achieved": achieved_contract,
                              "frac": achieved_contract / peak["tflops"],
                              "note": "SURVEY.md §8(d) figure (9-slot IEEE divisions, exp/log1p at every point)"},

@@ -89,6 +89,9 @@ typedef struct {
     double shell_r[IWB_MAX_SHELLS]; /* radii for the inclusive masks r <= R (the _e_at_r closure) */
     double *rho_out;           /* NULL, or [i_end-i_begin, n1, n2] doubles receiving rho_adm          */
     int32_t rho_out_is_device; /* 1: rho_out is a device pointer on the handle's device             */
+    int32_t tile_stride;       /* 0 or 1: every tile of the (j, k) plane.  S in {2, 4, 8, 16}: an interleaved */
+    int32_t tile_first;        /* tile shard, the tiles whose schedule index is tile_first (mod S) -- the     */
+                               /* multi-GPU decomposition (iwb_energy3d_tiles_async); rho_out must be NULL   */
 } iwb_params3d;
 
 typedef struct {
@@ -125,12 +128,28 @@ int iwb_energy3d(iwb_handle *h, const iwb_params3d *p, iwb_result *out);
  * stream) WITHOUT synchronising.  i_begin must be a multiple of IWB_FLUSH_PLANES. */
 int iwb_energy3d_slab_async(iwb_handle *h, const iwb_params3d *p, double *table_device, void *stream);
 
+/* Interleaved tile shards, the preferred multi-GPU decomposition: shard r of S (p->tile_first = r,
+ * p->tile_stride = S in {1, 2, 4, 8, 16}) evaluates every S-th tile of the (j, k) plane along the WHOLE of
+ * axis 0 -- no halo along axis 0, and every shard gets the same mix of face / wall / shell tiles.  The tile
+ * sums of a flush block are formed as IWB_TILE_CHAINS chains (chain c adds the tiles c, c + 16, ... of the
+ * schedule order) that a fixed binary tree combines; a shard owns the chains c = r (mod S) entirely and
+ * writes them to `chains_device`, [ceil(n0/IWB_FLUSH_PLANES)][IWB_TILE_CHAINS / S][IWB_ROW_WIDTH] doubles.
+ * After an all-gather (shard-major) iwb_reduce_chains applies the tree and the row sum: the same additions
+ * in the same order as the single-GPU path, so the result is bit-identical for every S.  No synchronisation. */
+#define IWB_TILE_CHAINS 16
+int iwb_energy3d_tiles_async(iwb_handle *h, const iwb_params3d *p, double *chains_device, void *stream);
+/* gathered_device: [S][nfb][IWB_TILE_CHAINS / S][IWB_ROW_WIDTH] (DEVICE).  Blocking: the scalars are on the host at return. */
+int iwb_reduce_chains(iwb_handle *h, const double *gathered_device, int tile_stride, int nfb, int nshell, void *stream,
+                      iwb_result *out);
+
 /* Prepared evaluation: coordinates uploaded and constants derived once, then launched any number
  * of times with NO host<->device traffic (kernel + tile reduction into `table_device` only).
  * This is what a resident-input measurement and a repeated-evaluation driver use.  rho_out, if
  * set, must be a device pointer. */
 typedef struct iwb_plan3d iwb_plan3d;
 int iwb_plan3d_create(iwb_handle *h, const iwb_params3d *p, iwb_plan3d **out);
+/* table_device: the slab table of iwb_energy3d_slab_async, or -- for a plan with tile_stride > 1 -- the chain
+ * buffer of iwb_energy3d_tiles_async. */
 int iwb_plan3d_run_async(iwb_plan3d *plan, double *table_device, void *stream);
 int iwb_plan3d_destroy(iwb_plan3d *plan);
 

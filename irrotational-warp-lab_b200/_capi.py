@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, os.path.basename(os.environ.get("IWB_LIB", "libiw
 
 MAX_SHELLS = 8
 FLUSH_PLANES = 16
+TILE_CHAINS = 16
 ROW_WIDTH = 6 + 3 * MAX_SHELLS
 
 OK, ERR_INVALID, ERR_GRID_TOO_SMALL, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM = range(6)
@@ -36,6 +37,7 @@ class Params3D(C.Structure):
         ("shell_r", C.c_double * MAX_SHELLS),
         ("rho_out", C.c_void_p),
         ("rho_out_is_device", C.c_int32),
+        ("tile_stride", C.c_int32), ("tile_first", C.c_int32),
     ]
 
 
@@ -110,6 +112,8 @@ SYMBOLS = {
                                   C.c_char_p, C.c_int]),
     "iwb_energy3d": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.POINTER(Result)]),
     "iwb_energy3d_slab_async": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.c_void_p, C.c_void_p]),
+    "iwb_energy3d_tiles_async": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.c_void_p, C.c_void_p]),
+    "iwb_reduce_chains": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(Result)]),
     "iwb_plan3d_create": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.POINTER(C.c_void_p)]),
     "iwb_plan3d_run_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "iwb_plan3d_destroy": (C.c_int, [C.c_void_p]),

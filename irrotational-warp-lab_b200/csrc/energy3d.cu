@@ -44,6 +44,11 @@ static int validate(const iwb_params3d* p)
         return fail(IWB_ERR_INVALID, "energy3d: i_begin must be a multiple of IWB_FLUSH_PLANES");
     if (p->nshell < 0 || p->nshell > IWB_MAX_SHELLS) return fail(IWB_ERR_INVALID, "energy3d: nshell out of range");
     if (!(p->dx > 0.0) || !(p->dy > 0.0) || !(p->dz > 0.0)) return fail(IWB_ERR_INVALID, "energy3d: spacings must be > 0");
+    const int ts = p->tile_stride;
+    if (!(ts == 0 || ts == 1 || ts == 2 || ts == 4 || ts == 8 || ts == 16))
+        return fail(IWB_ERR_INVALID, "energy3d: tile_stride must be 0, 1, 2, 4, 8 or 16");
+    if (p->tile_first < 0 || p->tile_first >= (ts > 1 ? ts : 1)) return fail(IWB_ERR_INVALID, "energy3d: need 0 <= tile_first < tile_stride");
+    if (ts > 1 && p->rho_out) return fail(IWB_ERR_INVALID, "energy3d: rho_out is not available for an interleaved tile shard");
     return IWB_OK;
 }
 
@@ -51,6 +56,7 @@ static int validate(const iwb_params3d* p)
 struct Launch3 {
     K3Params P;
     int dtype, mode, nshell, cfg_id, ntiles, fb0, fb1;
+    int tile_stride, tile_first;       // tile_stride > 1: interleaved tile shard (chain sums instead of table rows)
     bool emit;
 };
 
@@ -92,7 +98,10 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
 
     // work spans of the fused kernel (see k_energy3d), staged behind the coordinates
     const int ntj_ = (n1 + (cfg.rj - 4) - 1) / (cfg.rj - 4), ntk_ = (n2 + TK_MAX - 1) / TK_MAX;
-    const std::vector<int> spans = make_spans((long long)ntj_ * ntk_ * ((p->i_end - p->i_begin + FLUSH - 1) / FLUSH),
+    const int tstride = p->tile_stride > 1 ? p->tile_stride : 1, tfirst = p->tile_stride > 1 ? p->tile_first : 0;
+    const int ntiles_local = (ntj_ * ntk_ - tfirst + tstride - 1) / tstride;      // may be 0 on a tiny grid
+    const std::vector<int> spans = make_spans((long long)(ntiles_local > 0 ? ntiles_local : 0) *
+                                                  ((p->i_end - p->i_begin + FLUSH - 1) / FLUSH),
                                               h->sm_count, h->k3_static_pct);
     // coordinates: x, x*x, y*y, z*z (squares rounded once in the coordinate dtype, as x*x is in NumPy)
     const size_t ncoord = (size_t)2 * n0 + n1 + n2;
@@ -126,6 +135,7 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
     double* dc = (double*)coords.p;
     P.span_begin = (const int*)(dc + ncoord);
     P.nspans = (int)spans.size() - 1;
+    P.tile_first = tfirst; P.tile_stride = tstride;
     P.x = dc; P.xx = dc + n0; P.yy = dc + 2 * n0; P.zz = dc + 2 * n0 + n1;
     P.pc = make_phi_const(p->rho, p->sigma, p->v, p->eps, p->sinh_rs, p->cosh_rs);
     {
@@ -160,26 +170,35 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
     P.counter = (unsigned int*)counter.p;
     L->dtype = p->dtype; L->mode = p->mode; L->nshell = p->nshell; L->cfg_id = cfg_id; L->ntiles = ntiles; L->emit = rho_dev != nullptr;
     L->fb0 = p->i_begin / FLUSH; L->fb1 = (p->i_end + FLUSH - 1) / FLUSH;
+    L->tile_stride = tstride; L->tile_first = tfirst;
     return IWB_OK;
 }
 
 // Fused kernel + fixed-order tile reduction into rows [fb0, fb1) of `table`; no host<->device copy.
-static int launch_slab(iwb_handle* h, const Launch3& L, double* table, cudaStream_t st)
+// `table`: rows [fb0, fb1) of the [nfb][ROW] table, or (tiles_out) the shard's chain sums [nfb][CHAINS / stride][ROW].
+static int launch_slab(iwb_handle* h, const Launch3& L, double* table, cudaStream_t st, bool tiles_out = false)
 {
-    cudaError_t e = launch_k3(L.dtype, L.mode, L.nshell, L.emit, L.cfg_id, L.P, h->sm_count, st);
-    if (e != cudaSuccess) return fail(IWB_ERR_CUDA, std::string("k_energy3d launch: ") + cudaGetErrorString(e));
-    k_reduce_tiles<<<L.fb1 - L.fb0, 512, 0, st>>>(L.P.partial, table, L.fb0, L.ntiles, L.P.counter);
+    static_assert(IWB_TILE_CHAINS == 16, "k_reduce_tiles is launched with 16 chains");
+    if (L.P.nspans > 0) {
+        cudaError_t e = launch_k3(L.dtype, L.mode, L.nshell, L.emit, L.cfg_id, L.P, h->sm_count, st);
+        if (e != cudaSuccess) return fail(IWB_ERR_CUDA, std::string("k_energy3d launch: ") + cudaGetErrorString(e));
+    }
+    if (tiles_out)
+        k_chain_sums<<<L.fb1 - L.fb0, 32 * (IWB_TILE_CHAINS / L.tile_stride), 0, st>>>(
+            L.P.partial, table, L.fb0, L.ntiles, L.tile_first, L.tile_stride, IWB_TILE_CHAINS, L.P.counter);
+    else
+        k_reduce_tiles<<<L.fb1 - L.fb0, 32 * IWB_TILE_CHAINS, 0, st>>>(L.P.partial, table, L.fb0, L.ntiles, L.P.counter);
     IWB_CUDA(cudaGetLastError());
     return IWB_OK;
 }
 
 static int enqueue_slab(iwb_handle* h, Scratch& c, const iwb_params3d* p, double* table, cudaStream_t st,
-                        double* rho_dev)
+                        double* rho_dev, bool tiles_out = false)
 {
     Launch3 L;
     int rc = prepare_slab(h, p, c.h_coords, c.coords, c.partial, c.counter, st, rho_dev, &L);
     if (rc) return rc;
-    return launch_slab(h, L, table, st);
+    return launch_slab(h, L, table, st, tiles_out);
 }
 
 static void unpack_row(const double* row, int nshell, iwb_result* out)
@@ -199,6 +218,7 @@ static void unpack_row(const double* row, int nshell, iwb_result* out)
 // enqueue a full evaluation on scratch c; results land in c.h_out after c.ev1
 static int enqueue_full(iwb_handle* h, Scratch& c, const iwb_params3d* p)
 {
+    if (p->tile_stride > 1) return fail(IWB_ERR_INVALID, "an interleaved tile shard (tile_stride > 1) goes through iwb_energy3d_tiles_async");
     const int nfb_total = (p->n0 + FLUSH - 1) / FLUSH;
     IWB_CUDA(c.table.reserve((size_t)nfb_total * ROW * sizeof(double)));
     IWB_CUDA(c.out.reserve(ROW_BYTES_MIN));
@@ -267,6 +287,7 @@ int iwb_energy3d_slab_async(iwb_handle* h, const iwb_params3d* p, double* table_
     if (rc) return rc;
     if (p->rho_out && !p->rho_out_is_device)
         return fail(IWB_ERR_INVALID, "iwb_energy3d_slab_async: rho_out must be a device pointer");
+    if (p->tile_stride > 1) return fail(IWB_ERR_INVALID, "iwb_energy3d_slab_async: tile shards go through iwb_energy3d_tiles_async");
     IWB_CUDA(cudaSetDevice(h->device));
     Scratch& c = h->scr[0];
     cudaStream_t st = (cudaStream_t)stream;      // NULL is CUDA's default stream
@@ -292,12 +313,48 @@ int iwb_reduce_table(iwb_handle* h, const double* table_device, int nrows, int n
     return IWB_OK;
 }
 
+int iwb_energy3d_tiles_async(iwb_handle* h, const iwb_params3d* p, double* chains_device, void* stream)
+{
+    if (!h || !chains_device) return fail(IWB_ERR_INVALID, "iwb_energy3d_tiles_async: null argument");
+    int rc = validate(p);
+    if (rc) return rc;
+    if (p->rho_out) return fail(IWB_ERR_INVALID, "iwb_energy3d_tiles_async: rho_out must be NULL");
+    IWB_CUDA(cudaSetDevice(h->device));
+    Scratch& c = h->scr[0];
+    cudaStream_t st = (cudaStream_t)stream;      // NULL is CUDA's default stream
+    IWB_CUDA(cudaStreamSynchronize(st));         // the staging buffer of scratch 0 is reused
+    return enqueue_slab(h, c, p, chains_device, st, nullptr, true);
+}
+
+int iwb_reduce_chains(iwb_handle* h, const double* gathered_device, int tile_stride, int nfb, int nshell, void* stream,
+                      iwb_result* out)
+{
+    if (!h || !gathered_device || !out || nfb < 1) return fail(IWB_ERR_INVALID, "iwb_reduce_chains: bad argument");
+    if (!(tile_stride == 1 || tile_stride == 2 || tile_stride == 4 || tile_stride == 8 || tile_stride == 16))
+        return fail(IWB_ERR_INVALID, "iwb_reduce_chains: tile_stride must be 1, 2, 4, 8 or 16");
+    IWB_CUDA(cudaSetDevice(h->device));
+    Scratch& c = h->scr[0];
+    cudaStream_t st = (cudaStream_t)stream;
+    IWB_CUDA(c.table.reserve((size_t)nfb * ROW * sizeof(double)));
+    IWB_CUDA(c.out.reserve(ROW_BYTES_MIN));
+    IWB_CUDA(c.h_out.reserve(ROW_BYTES_MIN));
+    k_combine_chains<<<nfb, 32 * IWB_TILE_CHAINS, 0, st>>>(gathered_device, (double*)c.table.p, nfb, tile_stride);
+    k_reduce_rows<<<1, 128, 0, st>>>((const double*)c.table.p, (double*)c.out.p, nfb);
+    IWB_CUDA(cudaGetLastError());
+    IWB_CUDA(cudaMemcpyAsync(c.h_out.p, c.out.p, ROW_BYTES_MIN, cudaMemcpyDeviceToHost, st));
+    IWB_CUDA(cudaStreamSynchronize(st));
+    memset(out, 0, sizeof(*out));
+    unpack_row((const double*)c.h_out.p, nshell, out);
+    return IWB_OK;
+}
+
 int iwb_radial_profile3d(iwb_handle* h, const iwb_params3d* p, const iwb_profile3d* prof, iwb_result* out)
 {
     if (!h || !prof) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: null argument");
     int rc = validate(p);
     if (rc) return rc;
     if (p->rho_out) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: rho_out must be NULL (the field is staged internally)");
+    if (p->tile_stride > 1) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: not available for an interleaved tile shard");
     const int nb = prof->n_bins;
     if (nb < 1 || nb > PROF_MAX_BINS) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: n_bins must be in [1, 256]");
     if (!prof->edges || !prof->sum || !prof->count) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: edges / sum / count are NULL");
@@ -405,7 +462,7 @@ int iwb_plan3d_run_async(iwb_plan3d* plan, double* table_device, void* stream)
     if (!plan || !table_device) return fail(IWB_ERR_INVALID, "iwb_plan3d_run_async: null argument");
     IWB_CUDA(cudaSetDevice(plan->h->device));
     cudaStream_t st = (cudaStream_t)stream;      // NULL is CUDA's default stream
-    return launch_slab(plan->h, plan->L, table_device, st);
+    return launch_slab(plan->h, plan->L, table_device, st, plan->L.tile_stride > 1);
 }
 
 int iwb_plan3d_destroy(iwb_plan3d* plan)

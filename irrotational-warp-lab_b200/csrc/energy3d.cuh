@@ -62,8 +62,9 @@ struct K3Params {
     int i_begin, i_end;            // planes to evaluate (global indices)
     int ntj, ntk;                  // tiles of the (j, k) plane
     int nfb_slab;                  // flush blocks (FLUSH planes each) in [i_begin, i_end)
+    int tile_first, tile_stride;   // this launch covers the tiles of schedule index tile_first + m * tile_stride
     int nspans;                    // work spans, handed out dynamically in index order
-    const int* span_begin;         // [nspans + 1] unit boundaries; unit u = tile rank * nfb_slab + flush block
+    const int* span_begin;         // [nspans + 1] unit boundaries; unit u = m * nfb_slab + flush block
     const double* x;               // [n0]  (float32 values widened for the f32ref path)
     const double* xx;              // [n0]  x*x   (rounded in the path's coordinate dtype)
     const double* yy;              // [n1]  y*y
@@ -165,8 +166,9 @@ k_energy3d(const __grid_constant__ K3Params P)
     const int unit_end = P.span_begin[span + 1];
     while (unit < unit_end) {
         __syncthreads();                 // previous item's shared memory is dead
-        const int rnk = unit / P.nfb_slab;
-        const int fblk0 = unit - rnk * P.nfb_slab;
+        const int rnk_local = unit / P.nfb_slab;
+        const int fblk0 = unit - rnk_local * P.nfb_slab;
+        const int rnk = P.tile_first + rnk_local * P.tile_stride;      // schedule index of the tile
         const int fblk1 = min(P.nfb_slab, fblk0 + (unit_end - unit));
         unit += fblk1 - fblk0;
         // Tiles that touch a global face cost more than interior tiles (one-sided formulas, divergent lanes); they come
@@ -577,7 +579,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                         acc = __longlong_as_double(__double_as_longlong(acc) -
                                                    (long long)Tj * (RK - Tk) * (i_last - flush_from + 1));
                 }
-                P.partial[((size_t)fb * ntiles + tile) * ROW + slot] = acc;
+                P.partial[((size_t)fb * ntiles + rnk) * ROW + slot] = acc;     // slot of the tile's schedule index
             }
             // the scratch is rewritten at the next flush only, at least one step barrier from here
             acc_sum = 0.0; acc_abs = 0.0; cnt3 = 0;
@@ -647,37 +649,37 @@ k_energy3d(const __grid_constant__ K3Params P)
 
 // ---- fixed-order sum over tiles: partial[fb][tile][ROW] -> table[fb][ROW] ----------------------
 // (static: every translation unit that includes this header gets its own copy)
-// One block per flush block, blockDim.x = 32 * NCH threads (NCH a power of two <= 32): thread (slot q, chain c) adds the
-// tiles t = c, c + NCH, c + 2 NCH, ... in increasing order, then the chains are combined by a fixed binary tree in
-// shared memory.  Deterministic and independent of the slab decomposition (a flush block always sees the same tiles).
-// With 16 chains the 522 tiles of n = 1024 are 33 dependent additions per thread instead of 131.
+// The tiles of a flush block (slots in schedule order) are added as NCH chains -- chain c adds the slots c, c + NCH,
+// c + 2 NCH, ... in increasing order -- which a fixed binary tree then combines.  Deterministic and independent of
+// the decomposition: a slab sees all tiles of its flush blocks, an interleaved tile shard (stride S | NCH) owns whole
+// chains.  k_reduce_tiles does both steps in one block per flush block (blockDim.x = 32 * NCH, one slot per lane);
+// k_chain_sums / k_combine_chains are the two halves around the all-gather of the tile-shard path and perform the
+// same additions in the same order.  With 16 chains the 522 tiles of n = 1024 are 33 dependent additions per thread.
 static_assert(ROW <= 32, "one slot per lane");
-static __global__ void __launch_bounds__(1024) k_reduce_tiles(const double* __restrict__ partial,
-                                                              double* __restrict__ table, int fb_begin, int ntiles,
-                                                              unsigned int* counter = nullptr)
+__device__ __forceinline__ bool row_slot_is_int(int q) { return (q >= 2 && q < 6) || (q >= 6 + 2 * IWB_MAX_SHELLS); }
+
+// sum of the slots c, c + nch, ... of `src` (= partial + fb * ntiles * ROW + q), as a double or as int64 bits
+__device__ __forceinline__ double chain_sum(const double* __restrict__ src, int ntiles, int c, int nch, bool is_int)
 {
-    __shared__ double s_part[32][33];
-    if (counter && blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;    // re-arm the work queue of k_energy3d
-    const int fb = fb_begin + blockIdx.x;
-    const int q = threadIdx.x & 31, c = threadIdx.x >> 5, nch = blockDim.x >> 5;
-    const bool is_int = (q >= 2 && q < 6) || (q >= 6 + 2 * IWB_MAX_SHELLS);
     double a = 0.0;
     long long ia = 0;
-    if (q < ROW) {
-        const double* src = partial + (size_t)fb * ntiles * ROW + q;
-        int t = c;
-        for (; t + 3 * nch < ntiles; t += 4 * nch) {      // four loads in flight, added in tile order
-            const double v0 = src[(size_t)t * ROW], v1 = src[(size_t)(t + nch) * ROW];
-            const double v2 = src[(size_t)(t + 2 * nch) * ROW], v3 = src[(size_t)(t + 3 * nch) * ROW];
-            if (is_int) ia += __double_as_longlong(v0) + __double_as_longlong(v1) + __double_as_longlong(v2) + __double_as_longlong(v3);
-            else { a += v0; a += v1; a += v2; a += v3; }
-        }
-        for (; t < ntiles; t += nch) {
-            const double v = src[(size_t)t * ROW];
-            if (is_int) ia += __double_as_longlong(v); else a += v;
-        }
+    int t = c;
+    for (; t + 3 * nch < ntiles; t += 4 * nch) {      // four loads in flight, added in tile order
+        const double v0 = src[(size_t)t * ROW], v1 = src[(size_t)(t + nch) * ROW];
+        const double v2 = src[(size_t)(t + 2 * nch) * ROW], v3 = src[(size_t)(t + 3 * nch) * ROW];
+        if (is_int) ia += __double_as_longlong(v0) + __double_as_longlong(v1) + __double_as_longlong(v2) + __double_as_longlong(v3);
+        else { a += v0; a += v1; a += v2; a += v3; }
     }
-    s_part[c][q] = is_int ? __longlong_as_double(ia) : a;
+    for (; t < ntiles; t += nch) {
+        const double v = src[(size_t)t * ROW];
+        if (is_int) ia += __double_as_longlong(v); else a += v;
+    }
+    return is_int ? __longlong_as_double(ia) : a;
+}
+
+// binary tree over the chains held in s_part[c][q]; result in s_part[0][q]
+__device__ __forceinline__ void chain_tree(double (*s_part)[33], int q, int c, int nch, bool is_int)
+{
     __syncthreads();
     for (int h = nch >> 1; h > 0; h >>= 1) {
         if (c < h) {
@@ -686,6 +688,48 @@ static __global__ void __launch_bounds__(1024) k_reduce_tiles(const double* __re
         }
         __syncthreads();
     }
+}
+
+static __global__ void __launch_bounds__(1024) k_reduce_tiles(const double* __restrict__ partial,
+                                                              double* __restrict__ table, int fb_begin, int ntiles,
+                                                              unsigned int* counter = nullptr)
+{
+    __shared__ double s_part[32][33];
+    if (counter && blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;    // re-arm the work queue of k_energy3d
+    const int fb = fb_begin + blockIdx.x;
+    const int q = threadIdx.x & 31, c = threadIdx.x >> 5, nch = blockDim.x >> 5;
+    const bool is_int = row_slot_is_int(q);
+    s_part[c][q] = (q < ROW) ? chain_sum(partial + (size_t)fb * ntiles * ROW + q, ntiles, c, nch, is_int) : 0.0;
+    chain_tree(s_part, q, c, nch, is_int);
+    if (c == 0 && q < ROW) table[(size_t)fb * ROW + q] = s_part[0][q];
+}
+
+// tile-shard path, first half: the chains c = first + lc * stride (lc = 0 .. NCH/stride - 1) of every flush block
+// -> chains[fb][lc][ROW].  One block per flush block, blockDim.x = 32 * NCH / stride.
+static __global__ void __launch_bounds__(1024) k_chain_sums(const double* __restrict__ partial, double* __restrict__ chains,
+                                                            int fb_begin, int ntiles, int first, int stride, int nch,
+                                                            unsigned int* counter = nullptr)
+{
+    if (counter && blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;
+    const int fb = fb_begin + blockIdx.x;
+    const int q = threadIdx.x & 31, lc = threadIdx.x >> 5, nlc = blockDim.x >> 5;
+    if (q >= ROW) return;
+    const double v = chain_sum(partial + (size_t)fb * ntiles * ROW + q, ntiles, first + lc * stride, nch, row_slot_is_int(q));
+    chains[((size_t)fb * nlc + lc) * ROW + q] = v;
+}
+
+// tile-shard path, second half: gathered[shard][fb][lc][ROW] -> table[fb][ROW]; chain c is entry lc = c / stride of
+// shard c % stride.  One block per flush block, blockDim.x = 32 * NCH.
+static __global__ void __launch_bounds__(1024) k_combine_chains(const double* __restrict__ gathered, double* __restrict__ table,
+                                                                int nfb, int stride)
+{
+    __shared__ double s_part[32][33];
+    const int fb = blockIdx.x;
+    const int q = threadIdx.x & 31, c = threadIdx.x >> 5, nch = blockDim.x >> 5;
+    const int nlc = nch / stride;
+    const bool is_int = row_slot_is_int(q);
+    s_part[c][q] = (q < ROW) ? gathered[(((size_t)(c % stride) * nfb + fb) * nlc + c / stride) * ROW + q] : 0.0;
+    chain_tree(s_part, q, c, nch, is_int);
     if (c == 0 && q < ROW) table[(size_t)fb * ROW + q] = s_part[0][q];
 }
 

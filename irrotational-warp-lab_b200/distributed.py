@@ -1,9 +1,13 @@
 """One-process-per-GPU evaluation of a large 3D volume (torch.distributed over NCCL / NVLink).
 
 ``compute_energy_3d_sharded`` is the multi-GPU twin of ``backend.compute_energy_3d``: same
-arguments and return dictionary, but every rank evaluates one slab of axis 0 and the per-flush-
-block partial table is all-gathered (the only collective; 15 KB at n = 1024).  PyTorch is used
-for the device buffer of the table, the stream handle and the collective -- nothing else.
+arguments and return dictionary.  With 2, 4, 8 or 16 ranks every rank evaluates an interleaved
+shard of the (j, k) tiles along the whole of axis 0 and the per-flush-block chain sums are
+all-gathered (the only collective; 245 KB at n = 1024); otherwise (or with ``shard="slab"``) every
+rank evaluates one slab of axis 0 and the 15 KB partial table is all-gathered.  Either way every
+rank then performs the same fixed-order reduction, so the result is bit-identical to the
+single-GPU one.  PyTorch is used for the device buffers, the stream handle and the collective --
+nothing else.
 """
 from __future__ import annotations
 
@@ -12,13 +16,13 @@ import time
 import numpy as np
 
 from . import sharding
-from ._capi import ROW_WIDTH
+from ._capi import ROW_WIDTH, TILE_CHAINS
 from .backend import BACKEND_NAME, EPS, _ShellClosure, _grid, summary_metrics
 from .engine import get_engine
 
 
 def compute_energy_3d_sharded(*, rho, sigma, v, extent, n, dtype="float64", shells=None, group=None,
-                              device=None) -> dict:
+                              device=None, shard="auto") -> dict:
     import torch
     import torch.distributed as dist
 
@@ -27,8 +31,30 @@ def compute_energy_3d_sharded(*, rho, sigma, v, extent, n, dtype="float64", shel
     eng = get_engine(dev.index)
     x, dx = _grid(-extent, extent, n, dtype)
     shells = [8.0 * rho, 12.0 * rho] if shells is None else [float(s) for s in shells]
+    if shard not in ("auto", "tiles", "slab"):
+        raise ValueError(f"Unknown shard mode: {shard!r} (expected: auto|tiles|slab)")
+    tiles = None if shard == "slab" else sharding.tile_shard(world, rank)
+    if shard == "tiles" and tiles is None:
+        raise ValueError(f"shard='tiles' needs a world size that divides {TILE_CHAINS}, got {world}")
+
+    def evaluate_tiles(radii):
+        nfb = sharding.num_flush_blocks(n)
+        stride, first = tiles
+        local = torch.zeros((nfb, TILE_CHAINS // stride, ROW_WIDTH), dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev)
+        keep = eng.energy3d_tiles_async(local.data_ptr(), stream.cuda_stream, x=x, y=x, z=x, dx=dx, dy=dx, dz=dx,
+                                        rho=rho, sigma=sigma, v=v, dtype=dtype, shells=radii, eps=EPS,
+                                        tile_stride=stride, tile_first=first)
+        full = sharding.all_gather_chains(local, world, group=group) if world > 1 else local.unsqueeze(0)
+        res = eng.reduce_chains(full.data_ptr(), stride, nfb, len(radii), stream.cuda_stream)
+        res["cnt_nan"] = n ** 3 - res["cnt_pos"] - res["cnt_neg"] - res["cnt_zero"]
+        sharding.apply_reference_nonfinite(res)
+        del keep
+        return res
 
     def evaluate(radii):
+        if tiles is not None:
+            return evaluate_tiles(radii)
         nfb = sharding.num_flush_blocks(n)
         table = torch.zeros((nfb, ROW_WIDTH), dtype=torch.float64, device=dev)
         i_begin, i_end = sharding.slab_bounds(n, world)[rank]
@@ -59,6 +85,7 @@ def compute_energy_3d_sharded(*, rho, sigma, v, extent, n, dtype="float64", shel
         "counts": {"pos": res["cnt_pos"], "neg": res["cnt_neg"], "zero": res["cnt_zero"], "nan": res["cnt_nan"],
                    "shell_points": dict(zip(shells, res["shell_cnt"]))},
         "engine": {"name": "irrotational-warp-lab_b200", "device": eng.name, "world_size": world,
-                   "slab": list(sharding.slab_bounds(n, world)[rank])},
+                   "shard": "tiles" if tiles is not None else "slab",
+                   "slab": [0, n] if tiles is not None else list(sharding.slab_bounds(n, world)[rank])},
         "_e_at_r": _ShellClosure(lambda radii, out=None: evaluate(radii), known),
     }

@@ -50,7 +50,8 @@ class Engine:
     # -- 3D ---------------------------------------------------------------------------------
     @staticmethod
     def make_params3d(*, x, y, z, dx, dy, dz, rho, sigma, v, dtype, shells=(), eps=1e-12,
-                      i_begin=0, i_end=None, rho_out=None, rho_out_is_device=False, mode="exact"):
+                      i_begin=0, i_end=None, rho_out=None, rho_out_is_device=False, mode="exact",
+                      tile_stride=1, tile_first=0):
         """Fill an ``iwb_params3d``.  ``x, y, z`` are the host linspace arrays (float32 grids are
         widened to float64 without change of value).  Returns (params, keepalive)."""
         xd, yd, zd = _as_f64(x), _as_f64(y), _as_f64(z)
@@ -73,6 +74,7 @@ class Engine:
         p.nshell = len(shells)
         for s, r in enumerate(shells):
             p.shell_r[s] = r
+        p.tile_stride, p.tile_first = int(tile_stride), int(tile_first)     # interleaved tile shard (multi-GPU)
         keep = [xd, yd, zd]
         if rho_out is not None:
             if rho_out_is_device:
@@ -141,6 +143,22 @@ class Engine:
         _capi.check(self._lib.iwb_energy3d_slab_async(self._h, C.byref(p), C.c_void_p(int(table_ptr)),
                                                       C.c_void_p(int(stream_ptr or 0))))
         return keep
+
+    def energy3d_tiles_async(self, chains_ptr, stream_ptr=None, **kw):
+        """Interleaved tile shard ``tile_first`` of ``tile_stride``: chain sums into the device buffer
+        ``[nfb, TILE_CHAINS // tile_stride, ROW_WIDTH]`` (iwb_energy3d_tiles_async); no synchronisation."""
+        p, keep = self.make_params3d(**kw)
+        _capi.check(self._lib.iwb_energy3d_tiles_async(self._h, C.byref(p), C.c_void_p(int(chains_ptr)),
+                                                       C.c_void_p(int(stream_ptr or 0))))
+        return keep
+
+    def reduce_chains(self, gathered_ptr, tile_stride, nfb, nshell, stream_ptr=None):
+        """Fixed tree over the gathered chain sums ``[tile_stride, nfb, TILE_CHAINS // tile_stride, ROW_WIDTH]`` and the
+        row sum (iwb_reduce_chains); blocking."""
+        r = _capi.Result()
+        _capi.check(self._lib.iwb_reduce_chains(self._h, C.c_void_p(int(gathered_ptr)), int(tile_stride), int(nfb),
+                                                int(nshell), C.c_void_p(int(stream_ptr or 0)), C.byref(r)))
+        return self._result_dict(r, nshell)
 
     def plan3d(self, **kw):
         """Prepared evaluation (coordinates resident on the device); see :class:`Plan3D`."""

@@ -12,6 +12,13 @@ the B200-side design for BASELINE config 4 (n = 1024^3 on 1/2/4/8 GPUs):
   (``ceil(n0/16) x 30`` doubles, 15 KB at n = 1024), after which every rank adds the rows in the
   same fixed order -- so the energies are bit-identical for 1, 2, 4 or 8 ranks.
 
+The preferred decomposition for 2, 4, 8 or 16 ranks is by *interleaved tile shards* instead: rank r evaluates
+every P-th tile of the (j, k) plane along the whole of axis 0 (no halo along axis 0, and every rank gets the same
+mix of face, wall and shell tiles).  The tile sums of a flush block are 16 chains combined by a fixed binary tree;
+a rank owns whole chains, so all-gathering the chain sums (245 KB at n = 1024) and applying the tree on every rank
+again gives bit-identical energies for 1, 2, 4, 8 or 16 ranks (``tile_shard``, ``all_gather_chains``,
+``combine_chains_host``).
+
 Pure host logic; imports neither CUDA nor the oracle, and is exercised on CPU with gloo.
 """
 from __future__ import annotations
@@ -20,7 +27,7 @@ import math
 
 import numpy as np
 
-from ._capi import FLUSH_PLANES, MAX_SHELLS, ROW_WIDTH
+from ._capi import FLUSH_PLANES, MAX_SHELLS, ROW_WIDTH, TILE_CHAINS
 
 # row layout (include/iwb200.h): e_pos e_neg cnt_pos cnt_neg cnt_zero cnt_nan | shell_pos[8] shell_neg[8] shell_cnt[8]
 INT_SLOTS = np.array([2, 3, 4, 5] + list(range(6 + 2 * MAX_SHELLS, ROW_WIDTH)))
@@ -132,3 +139,44 @@ def all_gather_table(local_rows: "torch.Tensor", n0: int, world_size: int, group
     gathered = torch.empty((world_size, width, ROW_WIDTH), dtype=torch.float64, device=local_rows.device)
     dist.all_gather_into_tensor(gathered.view(-1), padded.view(-1), group=group)
     return torch.cat([gathered[r, : counts[r]] for r in range(world_size)], dim=0)
+
+
+# ---- interleaved tile shards ---------------------------------------------------------------------------------
+
+def tile_shard(world_size: int, rank: int) -> tuple[int, int] | None:
+    """(tile_stride, tile_first) of ``rank``, or None when ``world_size`` does not divide the number of chains
+    (then the slab decomposition is used)."""
+    if world_size >= 1 and TILE_CHAINS % world_size == 0:
+        return (world_size, rank)
+    return None
+
+
+def all_gather_chains(local: "torch.Tensor", world_size: int, group=None) -> "torch.Tensor":
+    """All-gather of the per-rank chain sums ``[nfb, TILE_CHAINS // P, ROW_WIDTH]`` into the rank-major
+    ``[P, nfb, TILE_CHAINS // P, ROW_WIDTH]`` buffer that ``iwb_reduce_chains`` / ``combine_chains_host`` read."""
+    import torch
+    import torch.distributed as dist
+
+    full = torch.empty((world_size,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(full.view(-1), local.contiguous().view(-1), group=group)
+    return full
+
+
+def combine_chains_host(gathered: np.ndarray) -> np.ndarray:
+    """Host twin of ``k_combine_chains`` (csrc/energy3d.cuh): ``[P, nfb, TILE_CHAINS // P, ROW_WIDTH]`` chain sums ->
+    the ``[nfb, ROW_WIDTH]`` table.  Chain c is entry ``c // P`` of rank ``c % P``; the chains are combined by the
+    binary tree s[c] += s[c + h], h = 8, 4, 2, 1 -- float slots as float64 additions, integer slots as int64."""
+    g = np.ascontiguousarray(gathered, dtype=np.float64)
+    P, nfb, nlc, width = g.shape
+    assert width == ROW_WIDTH and P * nlc == TILE_CHAINS
+    s = np.empty((TILE_CHAINS, nfb, ROW_WIDTH), dtype=np.float64)
+    for c in range(TILE_CHAINS):
+        s[c] = g[c % P, :, c // P, :]
+    si = s.view(np.int64)
+    h = TILE_CHAINS // 2
+    while h > 0:
+        for c in range(h):
+            s[c][:, FLOAT_SLOTS] = s[c][:, FLOAT_SLOTS] + s[c + h][:, FLOAT_SLOTS]
+            si[c][:, INT_SLOTS] = si[c][:, INT_SLOTS] + si[c + h][:, INT_SLOTS]
+        h //= 2
+    return s[0].copy()

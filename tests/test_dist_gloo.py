@@ -83,3 +83,60 @@ def test_two_and_three_ranks_match_golden_and_each_other(tmp_path):
     # shard-count independence: identical table, identical sums, to the last bit
     assert r2["table_hex"] == r3["table_hex"]
     assert r2["e_pos"] == r3["e_pos"] and r2["e_neg"] == r3["e_neg"] and r2["shell_pos"] == r3["shell_pos"]
+
+
+# ---- interleaved tile shards: gather layout and chain tree ---------------------------------------------------
+
+def _chain_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from irrotational_warp_lab_b200 import sharding
+        from irrotational_warp_lab_b200._capi import ROW_WIDTH, TILE_CHAINS
+        nfb = 5
+        chains = _synthetic_chains(nfb)                                   # [TILE_CHAINS, nfb, ROW_WIDTH], same on every rank
+        stride, first = sharding.tile_shard(world, rank)
+        assert (stride, first) == (world, rank)
+        mine = np.stack([chains[first + lc * stride] for lc in range(TILE_CHAINS // stride)], axis=1)   # [nfb, nlc, ROW]
+        full = sharding.all_gather_chains(torch.from_numpy(np.ascontiguousarray(mine)), world)
+        assert tuple(full.shape) == (world, nfb, TILE_CHAINS // world, ROW_WIDTH)
+        table = sharding.combine_chains_host(full.numpy())
+        if rank == 0:
+            json.dump([float(v).hex() for v in table.reshape(-1)], open(out_path, "w"))
+    finally:
+        dist.destroy_process_group()
+
+
+def _synthetic_chains(nfb):
+    from irrotational_warp_lab_b200 import sharding
+    from irrotational_warp_lab_b200._capi import ROW_WIDTH, TILE_CHAINS
+    rng = np.random.default_rng(7)
+    chains = rng.standard_normal((TILE_CHAINS, nfb, ROW_WIDTH)) * 10.0 ** rng.integers(-8, 8, (TILE_CHAINS, nfb, ROW_WIDTH))
+    chains.view(np.int64)[..., sharding.INT_SLOTS] = rng.integers(0, 1 << 40, (TILE_CHAINS, nfb, len(sharding.INT_SLOTS)))
+    return chains
+
+
+def test_chain_gather_is_world_size_independent(tmp_path):
+    """all_gather_chains + combine_chains_host with 1 (no collective), 2 and 4 gloo ranks: the same table to the last
+    bit, and equal to the tree written out by hand."""
+    from irrotational_warp_lab_b200 import sharding
+    from irrotational_warp_lab_b200._capi import TILE_CHAINS
+    nfb = 5
+    chains = _synthetic_chains(nfb)
+    s = [chains[c].copy() for c in range(TILE_CHAINS)]
+    h = TILE_CHAINS // 2
+    while h:
+        for c in range(h):
+            f, i = sharding.FLOAT_SLOTS, sharding.INT_SLOTS
+            s[c][:, f] = s[c][:, f] + s[c + h][:, f]
+            s[c].view(np.int64)[:, i] = s[c].view(np.int64)[:, i] + s[c + h].view(np.int64)[:, i]
+        h //= 2
+    want = [float(v).hex() for v in s[0].reshape(-1)]
+    one = sharding.combine_chains_host(np.stack([chains[c] for c in range(TILE_CHAINS)], axis=1)[None])
+    assert [float(v).hex() for v in one.reshape(-1)] == want
+    for world in (2, 4):
+        out = str(tmp_path / f"chains_{world}.json")
+        mp.spawn(_chain_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert json.load(open(out)) == want
+    assert sharding.tile_shard(3, 0) is None and sharding.tile_shard(16, 5) == (16, 5)
