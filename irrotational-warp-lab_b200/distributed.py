@@ -40,7 +40,7 @@ def compute_energy_3d_sharded(*, rho, sigma, v, extent, n, dtype="float64", shel
     def evaluate_tiles(radii):
         nfb = sharding.num_flush_blocks(n)
         stride, first = tiles
-        local = torch.zeros((nfb, TILE_CHAINS // stride, ROW_WIDTH), dtype=torch.float64, device=dev)
+        local = torch.empty((nfb, TILE_CHAINS // stride, ROW_WIDTH), dtype=torch.float64, device=dev)   # fully written
         stream = torch.cuda.current_stream(dev)
         keep = eng.energy3d_tiles_async(local.data_ptr(), stream.cuda_stream, x=x, y=x, z=x, dx=dx, dy=dx, dz=dx,
                                         rho=rho, sigma=sigma, v=v, dtype=dtype, shells=radii, eps=EPS,
