@@ -290,9 +290,11 @@ def main(argv=None):
         except OSError:
             pass
         hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
-        # coordinates in; per-(flush block, tile) partial rows out (36 x 60 tiles of the default 40 x 64 geometry);
+        # coordinates in; per-(flush block, tile) partial rows out (36 x 60 tiles of the default 40 x 64 geometry, 62 columns
+        # in the tiles at the k faces);
         # they are consumed by k_reduce_tiles and usually never leave L2
-        ntiles = -(-n // 36) * -(-n // 60)
+        ntk = 1 if n <= 64 else (2 if n <= 124 else 2 + -(-(n - 124) // 60))     # tiles_k (csrc/energy3d.cuh)
+        ntiles = -(-n // 36) * ntk
         alg_bytes = 8.0 * (2 * n + n + n) + 8.0 * ROW_WIDTH * (r1 - r0) * ntiles / (world if tiles is not None else 1)
         line = {
             "metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": steps, "warmup": warmup,

@@ -97,7 +97,7 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
     const K3Config cfg = kConfigs[cfg_id];
 
     // work spans of the fused kernel (see k_energy3d), staged behind the coordinates
-    const int ntj_ = (n1 + (cfg.rj - 4) - 1) / (cfg.rj - 4), ntk_ = (n2 + TK_MAX - 1) / TK_MAX;
+    const int ntj_ = (n1 + (cfg.rj - 4) - 1) / (cfg.rj - 4), ntk_ = tiles_k(n2);
     const int tstride = p->tile_stride > 1 ? p->tile_stride : 1, tfirst = p->tile_stride > 1 ? p->tile_first : 0;
     const int ntiles_local = (ntj_ * ntk_ - tfirst + tstride - 1) / tstride;      // may be 0 on a tiny grid
     const std::vector<int> spans = make_spans((long long)(ntiles_local > 0 ? ntiles_local : 0) *
@@ -127,7 +127,7 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
     P.n0 = n0; P.n1 = n1; P.n2 = n2;
     P.i_begin = p->i_begin; P.i_end = p->i_end;
     P.ntj = (n1 + (cfg.rj - 4) - 1) / (cfg.rj - 4);
-    P.ntk = (n2 + TK_MAX - 1) / TK_MAX;
+    P.ntk = tiles_k(n2);
     const int ntiles = P.ntj * P.ntk;
     const int planes = p->i_end - p->i_begin;
     const int nfb_slab = (planes + FLUSH - 1) / FLUSH;

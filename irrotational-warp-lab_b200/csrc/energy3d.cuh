@@ -83,6 +83,24 @@ struct K3Params {
 
 __host__ __device__ inline int tile_begin(int t, int nt, int n) { return (int)(((long long)t * n) / nt); }
 
+// Columns (k): an interior tile holds at most TK_MAX = RK - 4 output columns (2-column halo on either side), but the
+// tile at a global face needs no halo beyond the face and holds RK - 2 -- a single tile RK.  n = 1024 is 17 tiles
+// (2 x 62 + 15 x 60) instead of 18.  tiles_k: number of tiles; tile_begin_k: first column of tile t (t = nt: n), the
+// slack spread evenly over the tiles.
+__host__ __device__ inline int tiles_k(int n)
+{
+    if (n <= RK) return 1;
+    if (n <= 2 * (RK - 2)) return 2;
+    return 2 + (n - 2 * (RK - 2) + TK_MAX - 1) / TK_MAX;
+}
+__host__ __device__ inline int tile_begin_k(int t, int nt, int n)
+{
+    if (t <= 0) return 0;
+    if (t >= nt) return n;
+    const int slack = 2 * (RK - 2) + (nt - 2) * TK_MAX - n;
+    return (RK - 2) + (t - 1) * TK_MAX - (int)(((long long)t * slack) / nt);
+}
+
 template <int RJ, int NW>
 struct Geo {
     static constexpr int PLANE = RJ * RK;
@@ -190,7 +208,8 @@ k_energy3d(const __grid_constant__ K3Params P)
         }
         const int tj = tile / P.ntk, tk = tile - tj * P.ntk;
         const int j0 = tile_begin(tj, P.ntj, P.n1), Tj = tile_begin(tj + 1, P.ntj, P.n1) - j0;
-        const int k0 = tile_begin(tk, P.ntk, P.n2), Tk = tile_begin(tk + 1, P.ntk, P.n2) - k0;
+        const int k0 = tile_begin_k(tk, P.ntk, P.n2), Tk = tile_begin_k(tk + 1, P.ntk, P.n2) - k0;
+        const int hl = (k0 == 0) ? 0 : 2;           // halo columns on the low side: region column c is k = k0 - hl + c
         const int i0 = P.i_begin + fblk0 * FLUSH;
         const int i1 = min(P.i_end, P.i_begin + fblk1 * FLUSH);
 
@@ -208,11 +227,11 @@ k_energy3d(const __grid_constant__ K3Params P)
         double zz0, zz1;
         unsigned cf0, cf1;       // bit1 k==0, bit2 k==n2-1, bit4 output column
         {
-            const int ka = k0 - 2 + tx, kb = ka + 32;
+            const int ka = k0 - hl + tx, kb = ka + 32;
             zz0 = P.zz[min(max(ka, 0), P.n2 - 1)];
             zz1 = P.zz[min(max(kb, 0), P.n2 - 1)];
-            cf0 = ((ka == 0) ? 2u : 0u) | ((ka == P.n2 - 1) ? 4u : 0u) | ((tx >= 2 && tx <= Tk + 1) ? 16u : 0u);
-            cf1 = ((kb == 0) ? 2u : 0u) | ((kb == P.n2 - 1) ? 4u : 0u) | ((tx + 32 <= Tk + 1) ? 16u : 0u);
+            cf0 = ((ka == 0) ? 2u : 0u) | ((ka == P.n2 - 1) ? 4u : 0u) | ((tx >= hl && tx < hl + Tk) ? 16u : 0u);
+            cf1 = ((kb == 0) ? 2u : 0u) | ((kb == P.n2 - 1) ? 4u : 0u) | ((tx + 32 < hl + Tk) ? 16u : 0u);
         }
 
         // all-ones / zero words of the two columns: AND-mask of the energy density at non-output columns
@@ -389,7 +408,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                         rho2[a] = cdivm<MODE>(tr * tr - kk, P.c16pi, P.rc16pi);
                     }
                     if (EMIT) {
-                        const long long j = j0 - 2 + jr, k = k0 - 2 + tx;
+                        const long long j = j0 - 2 + jr, k = k0 - hl + tx;
                         double* dst = P.rho_out + ((long long)(i - P.i_begin) * P.n1 + j) * P.n2 + k;
                         if (cf0 & 16u) dst[0] = rho2[0];
                         if (cf1 & 16u) dst[32] = rho2[1];
