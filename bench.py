@@ -41,14 +41,16 @@ RHO, SIGMA, V, EXTENT = 5.0, 4.0, 1.0, 66.0
 SHELLS = [40.0, 60.0]
 METRIC = "3D Gpoints/s (fp64, n=1024^3)"
 # FP64 issue slots per grid point.  CONTRACT = SURVEY.md §8(d) / BASELINE.md §4 (IEEE divisions at 9 slots
-# each, exp/log1p on every point).  EXACT_ALG = the bit-exact algorithm this engine runs, counted from
-# SASS with ncu: constant-divisor divisions in 3 slots, exp/log1p only inside the wall.
+# each, exp/log1p on every point).  EXACT_ALG = the bit-exact algorithm this engine runs, each grid point
+# evaluated once (no halo recompute), from the ncu per-instruction counts of the hot loops divided by their
+# geometric redundancy: phi 35 (sqrt 8, two divisions 2 x 6, other 15), nine
+# derivatives x 4, rho*dV 19, sums 5.  The kernel EXECUTES 113 FP64 instructions per point (halo recompute).
 SLOTS_CONTRACT = 271.0
-SLOTS_EXACT_ALG = 114.0
+SLOTS_EXACT_ALG = 95.0
 CPU_SAMPLE_N = 256
 # dram__bytes_read.sum + dram__bytes_write.sum of k_energy3d, one launch at n = 1024^3 on one GPU, from the
-# committed `ncu --set full` capture of this command (profiles/r1_k_energy3d_n1024_final_summary.txt)
-NCU_DRAM_BYTES_PER_LAUNCH = 486912 + 3328
+# committed `ncu --set full` capture of the same kernel launch (profiles/r1_k_energy3d_n1024_session2_summary.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = 490496 + 0
 
 
 class ClockSampler:
@@ -317,8 +319,9 @@ def main(argv=None):
                 "achieved": achieved_exact, "peak": peak["tflops"], "frac": achieved_exact / peak["tflops"],
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (n == 1024 and world == 1) else None,
                 "slots_per_point": SLOTS_EXACT_ALG,
-                "note": "FP64-pipe bound: achieved = kernel points/s x 114 FP64 issue slots/point x 2 (slots of the "
-                        "bit-exact algorithm, counted from SASS, DESIGN.md §6); peak = register-resident DFMA "
+                "note": "FP64-pipe bound: achieved = kernel points/s x 95 FP64 issue slots/point x 2 (slots of the "
+                        "bit-exact algorithm with every point evaluated once, from ncu SASS counts, DESIGN.md §6; the "
+                        "kernel executes 113/point including the phi halo recompute); peak = register-resident DFMA "
                         "microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 vector figure)",
                 "kernel_ms": kern_ms_avg, "kernel_points": kernel_points,
                 "contract": {"slots_per_point": SLOTS_CONTRACT, "achieved": achieved_contract,
