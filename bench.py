@@ -24,6 +24,7 @@ Printed JSON (one line, rank 0):
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -215,6 +216,8 @@ def main(argv=None):
 
     for _ in range(warmup):
         res = resident_step()
+    gc.collect()
+    gc.disable()          # no collector pauses between the launches of the timed steps (one late rank delays every rank)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -228,7 +231,10 @@ def main(argv=None):
         ev[s][1].record(stream)
     barrier()
     t_region1 = time.perf_counter()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = sum(step_ms)
+    if os.environ.get("IWB_BENCH_VERBOSE"):
+        print(f"rank {rank} step ms: " + " ".join(f"{t:.3f}" for t in step_ms), file=sys.stderr, flush=True)
     if world > 1:
         t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -271,6 +277,7 @@ def main(argv=None):
         e2e_s = float(t.item())
     e2e_value = n ** 3 * steps / e2e_s / 1e9
     launches_e2e = steps * (4 if tiles is not None else 3)
+    gc.enable()
     if rank == 0:
         sampler.stop()
     clocks = sampler.summary(t_region0, time.perf_counter()) if rank == 0 else None
