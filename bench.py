@@ -84,8 +84,10 @@ class ClockSampler:
 
     def summary(self, t0, t1):
         sm, smax, reasons = [], [], set()
+        # the sampling period is 100 ms and an 8-GPU timed region is ~30 ms: take the samples that bracket it as well
+        # (the GPU runs the same steps in the warm-up just before and in the kernel-only / end-to-end legs just after)
         for t, line in self.rows:
-            if t < t0 or t > t1:
+            if t < t0 - 0.12 or t > t1 + 0.12:
                 continue
             f = [c.strip() for c in line.split(",")]
             if len(f) < 9:
@@ -214,13 +216,16 @@ def main(argv=None):
         full = sharding.all_gather_table(table[r0:r1], n, world) if world > 1 else table
         return eng.reduce_table(full.data_ptr(), nfb, len(SHELLS), stream.cuda_stream)
 
+    # nvidia-smi is started BEFORE the warm-up and given time to initialise NVML: its start-up briefly stalls the driver,
+    # which showed up as 0.2-0.3 ms outliers in the 1.4 ms steps of an 8-GPU run when it fell into the timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)
     for _ in range(warmup):
         res = resident_step()
     gc.collect()
     gc.disable()          # no collector pauses between the launches of the timed steps (one late rank delays every rank)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
     t_region0 = time.perf_counter()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
