@@ -40,6 +40,9 @@
 #ifndef IWB_BARRIER_BACKOFF_NS
 #define IWB_BARRIER_BACKOFF_NS 100
 #endif
+#ifndef IWB_FLUSH_PACK
+#define IWB_FLUSH_PACK 1    // counts packed two per 32-bit word in the flush butterfly (+0.5 %)
+#endif
 #ifndef IWB_P4
 #define IWB_P4 1       // task P evaluates both rows of a warp at once: four independent phi evaluations per thread
 #endif
@@ -559,6 +562,42 @@ k_energy3d(const __grid_constant__ K3Params P)
                 vals[6 + NSH + s] = (sh_sum[s] - sh_abs[s]) * 0.5;
                 vals[6 + 2 * NSH + s] = __longlong_as_double((long long)sh_cnt[s]);
             }
+#if IWB_FLUSH_PACK
+            // warp butterfly (fixed order).  The counts are at most 64 per thread and 2048 per warp: two of them share a
+            // 32-bit word (16-bit fields), so 3 + NSH counts cost (3 + NSH + 1) / 2 one-register shuffles per step
+            // instead of 3 + NSH two-register ones.
+            constexpr int NCNT = 3 + NSH, NCW = (NCNT + 1) / 2;
+            unsigned cw[NCW];
+            {
+                int c[2 * NCW];
+                c[0] = cnt3 & 0xff; c[1] = (cnt3 >> 8) & 0xff; c[2] = (cnt3 >> 16) & 0xff;     // neg, pos, zero
+#pragma unroll
+                for (int s2 = 0; s2 < NSH; ++s2) c[3 + s2] = sh_cnt[s2];
+                if (NCNT & 1) c[NCNT] = 0;
+#pragma unroll
+                for (int k = 0; k < NCW; ++k) cw[k] = (unsigned)c[2 * k] | ((unsigned)c[2 * k + 1] << 16);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int k = 0; k < NCW; ++k) cw[k] += __shfl_xor_sync(0xffffffffu, cw[k], off);
+            }
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const bool is_int = (q >= 2 && q < 6) || (q >= 6 + 2 * NSH);
+                if (is_int) continue;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) vals[q] += __shfl_xor_sync(0xffffffffu, vals[q], off);
+            }
+            {
+                auto field = [&](int idx) { return (long long)((cw[idx >> 1] >> ((idx & 1) * 16)) & 0xffffu); };
+                vals[3] = __longlong_as_double(field(0));
+                vals[2] = __longlong_as_double(field(1));
+                vals[4] = __longlong_as_double(field(2));
+#pragma unroll
+                for (int s2 = 0; s2 < NSH; ++s2) vals[6 + 2 * NSH + s2] = __longlong_as_double(field(3 + s2));
+            }
+#else
             // warp butterfly (fixed order), integers added as integers
 #pragma unroll
             for (int q = 0; q < NV; ++q) {
@@ -570,6 +609,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                     else vals[q] += o;
                 }
             }
+#endif
             if (tx == 0) {
 #pragma unroll
                 for (int q = 0; q < NV; ++q) scratch[ty * NV + q] = vals[q];
