@@ -239,6 +239,14 @@ int iwb_measure_fma_peak(iwb_handle *h, int use_fp32, double *tflops, double *sm
  * on `count` pseudo-random numerators; returns the number of mismatching results in *mismatches. */
 int iwb_selftest_constdiv(iwb_handle *h, double divisor, uint64_t count, uint64_t seed, uint64_t *mismatches);
 
+/* Host-only views of the fused kernel's work decomposition (no device needed; used by the CPU test-suite).
+ * iwb_debug_spans: the span boundaries over `units` work units for `ctas` persistent CTAs with `static_pct` % of
+ * the units in one large span per CTA (see k_energy3d); writes at most `cap` ints to `out`, returns the number of
+ * boundaries (spans + 1).  iwb_debug_tiles_k: the first column of each tile of an n-column axis, then n; returns
+ * the number of tiles (boundaries = tiles + 1), writing at most `cap` ints. */
+int iwb_debug_spans(long long units, int ctas, int static_pct, int *out, int cap);
+int iwb_debug_tiles_k(int n, int *out, int cap);
+
 /* Test hook: the branch-free division / square-root sequences of the exact kernels against the built-in
  * IEEE operators on `count` pseudo-random operand pairs (wide_exponents != 0 also exercises the range
  * check that routes exceptional operands to the built-in sequence; those pairs are counted in *skipped). */

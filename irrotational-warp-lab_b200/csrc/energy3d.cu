@@ -313,6 +313,22 @@ int iwb_reduce_table(iwb_handle* h, const double* table_device, int nrows, int n
     return IWB_OK;
 }
 
+int iwb_debug_spans(long long units, int ctas, int static_pct, int* out, int cap)
+{
+    const std::vector<int> b = make_spans(units, ctas, static_pct);
+    for (size_t q = 0; q < b.size() && (int)q < cap; ++q)
+        if (out) out[q] = b[q];
+    return (int)b.size();
+}
+
+int iwb_debug_tiles_k(int n, int* out, int cap)
+{
+    const int nt = tiles_k(n);
+    for (int t = 0; t <= nt && t < cap; ++t)
+        if (out) out[t] = tile_begin_k(t, nt, n);
+    return nt;
+}
+
 int iwb_energy3d_tiles_async(iwb_handle* h, const iwb_params3d* p, double* chains_device, void* stream)
 {
     if (!h || !chains_device) return fail(IWB_ERR_INVALID, "iwb_energy3d_tiles_async: null argument");

@@ -5,10 +5,12 @@
 // g_rodal_exact (/root/reference/src/irrotational_warp/potential.py:37-99); no
 // intermediate ever reaches HBM.
 //
-// Decomposition.  The volume is C-order [i, j, k] (k contiguous).  A work item is
-// (tile of the (j, k) plane) x (range of i planes); the CTA marches along i.
-// The CTA's region is the tile plus a 2-point halo: RJ rows (j) x 64 columns (k),
-// lanes along k.  Warp w owns region rows jr = w, w+NW, ...; lane tx owns columns tx, tx+32.
+// Decomposition.  The volume is C-order [i, j, k] (k contiguous).  A work unit is
+// (tile of the (j, k) plane) x (flush block of IWB_FLUSH_PLANES planes of i); a CTA takes spans of
+// consecutive units and marches along i (see "Work distribution" in the kernel).
+// The CTA's region is the tile plus a 2-point halo: RJ rows (j) x 64 columns (k), lanes along k
+// (tiles at the two k faces need no halo beyond the face and hold 62 instead of 60 columns).
+// Warp w owns region rows jr = w, w+NW, ...; lane tx owns columns tx, tx+32.
 //
 // Shared memory, 11 planes of RJ x 64 doubles:
 //     phi ring [3]   (plane q in slot q mod 3)
@@ -16,21 +18,24 @@
 //     phi_y, phi_z   double-buffered (plane q in buffer q mod 2)
 // The rings are sized so that ONE barrier per output plane suffices, and that barrier is split
 // (mbarrier arrive ... wait).  Per output plane i every warp runs
-//     O(i)  : second derivatives, rho, predicated sums of plane i             -- smem heavy, then FP64
-//     C(i+1): phi_y(i+1), phi_z(i+1) from the phi(i+1) plane                  -- smem heavy
+//     O(i) + C(i+1): second derivatives, rho, sums of plane i; phi_y(i+1), phi_z(i+1)   -- smem heavy, one row loop
 //     -- arrive --
-//     P(i+3): evaluate phi(i+3) at the own columns and finish phi_x(i+2)      -- FP64 heavy, ~no smem
+//     P(i+3): evaluate phi(i+3) at the own columns and finish phi_x(i+2)                -- FP64 heavy, ~no smem
 //     -- wait --
 // P touches only the own columns' ring entries until two steps later, so it is legal between the
 // arrival and the wait; warps drift apart by up to one task, and the shared-memory-bound tasks of
 // some warps overlap the FP64-bound task of others (measured: 59 -> 77 Gpoints/s over the version
 // with two __syncthreads per plane, whose smem and FP64 phases alternated in lock step).
-// Row loops are deliberately NOT unrolled (two columns of ILP per thread): the IEEE division / sqrt
-// sequences are long and an unrolled body overflows the instruction cache.
+// The tasks address shared memory explicitly (one laundered base address per thread, CTA-uniform plane
+// offsets, immediates for the neighbours) and evaluate the central formulas everywhere; rows / columns /
+// planes on a global face then override the affected derivatives with the one-sided formulas.
+// Row loops are deliberately NOT unrolled: the IEEE division / sqrt sequences are long and an unrolled
+// body overflows the instruction cache (task P alone handles both rows of a warp at once, for ILP).
 // Sums are kept in registers and flushed (warp shuffle + fixed-order block tree) once per
-// IWB_FLUSH_PLANES planes into partial[flush block][tile][row]; a second kernel adds the tiles in
-// fixed order.  Flush blocks are aligned to the GLOBAL plane index, so the result is bit-identical
-// for any slab decomposition along i.
+// IWB_FLUSH_PLANES planes into partial[flush block][tile slot][row]; a second kernel adds the tiles in
+// fixed order (16 chains + binary tree).  Flush blocks are aligned to the GLOBAL plane index and a tile
+// shard owns whole chains, so the result is bit-identical for any slab decomposition along i and any
+// interleaved tile sharding (DESIGN.md sections 4.2, 5).
 #pragma once
 #include <type_traits>
 

@@ -97,3 +97,48 @@ def test_product_never_imports_the_oracle():
            "irrotational_warp_lab_b200.optimize, irrotational_warp_lab_b200.distributed; " \
            "assert not any(m.startswith('oracle') for m in sys.modules), 'oracle imported'" % ROOT
     subprocess.check_call([sys.executable, "-c", code])
+
+
+def test_span_table_covers_every_unit_once():
+    """make_spans (csrc/energy3d.cu) through its host-only view: boundaries start at 0, end at `units`, increase
+    strictly, the first `ctas` spans carry the static share in equal parts, the last span is a single unit (it bounds
+    the scheduling tail), and a tiny problem degenerates to one unit per span."""
+    lib = _capi.load()
+    for units, ctas, pct in [(33408, 148, 70), (31552, 148, 70), (3968, 148, 70), (640, 148, 70), (12, 148, 70),
+                             (1, 148, 70), (0, 148, 70), (5000, 148, 0), (5000, 148, 100), (5000, 1, 70), (1 << 20, 148, 80)]:
+        n = lib.iwb_debug_spans(units, ctas, pct, None, 0)
+        buf = (C.c_int * max(n, 1))()
+        assert lib.iwb_debug_spans(units, ctas, pct, buf, n) == n
+        b = list(buf)[:n]
+        assert b[0] == 0 and b[-1] == units, (units, ctas, pct)
+        assert all(b[q] < b[q + 1] for q in range(n - 1)), (units, ctas, pct)
+        sizes = [b[q + 1] - b[q] for q in range(n - 1)]
+        if units >= 4 * ctas and 0 < pct:
+            static = sizes[:ctas]
+            assert sum(static) == units * pct // 100 and max(static) - min(static) <= 1
+            assert all(sizes[q] >= sizes[q + 1] for q in range(ctas, len(sizes) - 1))     # guided: never growing
+        if units > 0 and pct < 100:
+            assert sizes[-1] == 1
+        if 0 < units < 4 * ctas:
+            assert sizes == [1] * units
+
+
+def test_column_tiles_partition_the_axis():
+    """tiles_k / tile_begin_k (csrc/energy3d.cuh): interior tiles hold at most 60 output columns, the two tiles at
+    the global faces 62, a single tile 64; the tiles partition [0, n) and there is never one more than needed."""
+    lib = _capi.load()
+    buf = (C.c_int * 256)()
+    for n in list(range(3, 700)) + [1000, 1023, 1024, 1025, 2048, 4096, 5000]:
+        nt = lib.iwb_debug_tiles_k(n, buf, 256)
+        b = list(buf)[: nt + 1]
+        assert b[0] == 0 and b[-1] == n
+        sizes = [b[t + 1] - b[t] for t in range(nt)]
+        assert min(sizes) >= 1
+        if nt == 1:
+            assert n <= 64
+        else:
+            assert sizes[0] <= 62 and sizes[-1] <= 62 and all(s <= 60 for s in sizes[1:-1])
+            assert max(sizes) - min(sizes) <= 3            # the slack is spread evenly
+            cap_fewer = 64 if nt == 2 else 2 * 62 + (nt - 3) * 60
+            assert n > cap_fewer                           # one tile fewer would not hold n columns
+    assert lib.iwb_debug_tiles_k(1024, buf, 256) == 17 and list(buf)[:3] == [0, 62, 122]
