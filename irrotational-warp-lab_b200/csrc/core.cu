@@ -227,8 +227,8 @@ int iwb_create(int device_id, iwb_handle** out)
     const char* cfg = getenv("IWB_K3_CONFIG");
     h->k3_config = cfg ? atoi(cfg) : 1;
     const char* sp = getenv("IWB_K3_STATIC_PCT");
-    h->k3_static_pct = sp ? atoi(sp) : 70;
-    if (h->k3_static_pct < 0 || h->k3_static_pct > 100) h->k3_static_pct = 70;
+    h->k3_static_pct = sp ? atoi(sp) : -1;
+    if (h->k3_static_pct < -1 || h->k3_static_pct > 100) h->k3_static_pct = -1;
     *out = h;
     return IWB_OK;
 }

@@ -100,9 +100,12 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
     const int ntj_ = (n1 + (cfg.rj - 4) - 1) / (cfg.rj - 4), ntk_ = tiles_k(n2);
     const int tstride = p->tile_stride > 1 ? p->tile_stride : 1, tfirst = p->tile_stride > 1 ? p->tile_first : 0;
     const int ntiles_local = (ntj_ * ntk_ - tfirst + tstride - 1) / tstride;      // may be 0 on a tiny grid
+    // share of the units in the large spans: 80 % when the launch covers the whole of axis 0 (every CTA's span then
+    // mixes wall / shell / plain planes), 70 % for a slab (the slabs around the bubble wall are markedly heavier per unit)
+    const int static_pct = h->k3_static_pct >= 0 ? h->k3_static_pct : ((p->i_begin == 0 && p->i_end == n0) ? 80 : 70);
     const std::vector<int> spans = make_spans((long long)(ntiles_local > 0 ? ntiles_local : 0) *
                                                   ((p->i_end - p->i_begin + FLUSH - 1) / FLUSH),
-                                              h->sm_count, h->k3_static_pct);
+                                              h->sm_count, static_pct);
     // coordinates: x, x*x, y*y, z*z (squares rounded once in the coordinate dtype, as x*x is in NumPy)
     const size_t ncoord = (size_t)2 * n0 + n1 + n2;
     const size_t stage_bytes = ncoord * sizeof(double) + spans.size() * sizeof(int);

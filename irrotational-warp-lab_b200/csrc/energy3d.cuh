@@ -48,6 +48,9 @@
 #ifndef IWB_FLUSH_PACK
 #define IWB_FLUSH_PACK 1    // counts packed two per 32-bit word in the flush butterfly (+0.5 %)
 #endif
+#ifndef IWB_OC_UNROLL
+#define IWB_OC_UNROLL 1     // both rows of the O + C loop unrolled: no loop overhead, row b's loads overlap row a's tally (+0.9 %)
+#endif
 #ifndef IWB_P4
 #define IWB_P4 1       // task P evaluates both rows of a warp at once: four independent phi evaluations per thread
 #endif
@@ -353,7 +356,11 @@ k_energy3d(const __grid_constant__ K3Params P)
             const int iedge = (i == 0) ? 1 : ((i == P.n0 - 1) ? 2 : 0);
             const bool o_face = tile_edge || (iedge != 0);
             unsigned A = a_row0, ya = yy_row0;
+#if IWB_OC_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (int jr = ty; jr < RJ; jr += NW, A += ROWB, ya += NW * 8) {
                 const int jedge = (t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0);
                 if (doO && jr >= 2 && jr <= Tj + 1) {

@@ -95,7 +95,8 @@ struct iwb_handle {
     cudaDeviceProp prop;
     iwb::Scratch scr[iwb::NSCRATCH];
     int k3_config = 0;         // kernel geometry variant (IWB_K3_CONFIG env override)
-    int k3_static_pct = 70;    // share of the work units handed out as one large span per CTA (IWB_K3_STATIC_PCT env override)
+    int k3_static_pct = -1;    // share of the work units handed out as one large span per CTA; -1 = automatic (80 / 70 %),
+                               // IWB_K3_STATIC_PCT env override
 };
 
 namespace iwb {

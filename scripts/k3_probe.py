@@ -15,7 +15,7 @@ for rep in range(reps):
     r = eng.energy3d(x=x, y=x, z=x, dx=dx, dy=dx, dz=dx, rho=5.0, sigma=4.0, v=1.0, dtype=dtype, shells=[40.0, 60.0], mode=mode)
     ts.append(r["kernel_ms"])
 best = min(ts[1:]) if reps > 1 else ts[0]
-print(f"mode={mode} cfg={os.environ.get('IWB_K3_CONFIG','default')} static_pct={os.environ.get('IWB_K3_STATIC_PCT','70')} n={n} {dtype} best {best:.3f} ms "
+print(f"mode={mode} cfg={os.environ.get('IWB_K3_CONFIG','default')} static_pct={os.environ.get('IWB_K3_STATIC_PCT','auto')} n={n} {dtype} best {best:.3f} ms "
       f"{n**3/best/1e6:.2f} Gpts/s all={['%.2f'%t for t in ts]} e_pos={r['e_pos']!r} neg={r['cnt_neg']}", flush=True)
 
 if len(sys.argv) > 4:      # slab probe: planes [a, b)

@@ -22,5 +22,5 @@ for r in range(P):
         a.record(st); plan.run_async(buf.data_ptr(), st.cuda_stream); b.record(st); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     out.append(min(ts[1:])); plan.close()
-print(f"static_pct={os.environ.get('IWB_K3_STATIC_PCT','70')} tile shards P={P} ms: " + " ".join(f"{t:.3f}" for t in out) +
+print(f"static_pct={os.environ.get('IWB_K3_STATIC_PCT','auto')} tile shards P={P} ms: " + " ".join(f"{t:.3f}" for t in out) +
       f"  max {max(out):.3f} mean {sum(out)/len(out):.3f} ideal {10.14/P:.3f}", flush=True)

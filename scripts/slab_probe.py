@@ -16,4 +16,4 @@ for r in range(P):
         res = eng.energy3d(x=x, y=x, z=x, dx=dx, dy=dx, dz=dx, rho=5.0, sigma=4.0, v=1.0, dtype="float64", shells=[40.0, 60.0], i_begin=a, i_end=b)
         ts.append(res["kernel_ms"])
     out.append(min(ts[1:]))
-print(f"static_pct={os.environ.get("IWB_K3_STATIC_PCT","70")} P={P} slab ms: " + " ".join(f"{t:.3f}" for t in out) + f"  max {max(out):.3f} mean {sum(out)/len(out):.3f}", flush=True)
+print(f"static_pct={os.environ.get("IWB_K3_STATIC_PCT","auto")} P={P} slab ms: " + " ".join(f"{t:.3f}" for t in out) + f"  max {max(out):.3f} mean {sum(out)/len(out):.3f}", flush=True)
