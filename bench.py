@@ -51,7 +51,9 @@ SLOTS_EXACT_ALG = 95.0
 CPU_SAMPLE_N = 256
 # dram__bytes_read.sum + dram__bytes_write.sum of k_energy3d, one launch at n = 1024^3 on one GPU, from the
 # committed `ncu --set full` capture of the same kernel launch (profiles/r1_k_energy3d_n1024_session2_summary.txt)
-NCU_DRAM_BYTES_PER_LAUNCH = 490496 + 0
+# (111 616 B read, 0 B written in the capture of the final kernel; 490 496 B in the one before -- coordinate and
+# instruction fetches, it varies with the state of the L2)
+NCU_DRAM_BYTES_PER_LAUNCH = 111616 + 0
 
 
 class ClockSampler:
