@@ -142,6 +142,13 @@ int iwb_energy3d_tiles_async(iwb_handle *h, const iwb_params3d *p, double *chain
 int iwb_reduce_chains(iwb_handle *h, const double *gathered_device, int tile_stride, int nfb, int nshell, void *stream,
                       iwb_result *out);
 
+/* Non-blocking halves of iwb_reduce_table / iwb_reduce_chains for callers that keep several evaluations in flight on one
+ * stream: the final row (IWB_ROW_WIDTH doubles, layout of the table rows) is left in `row_device`; nothing is copied to
+ * the host and nothing is synchronised.  `table_scratch_device` receives the [nfb][IWB_ROW_WIDTH] table of the chain tree. */
+int iwb_reduce_table_async(iwb_handle *h, const double *table_device, int nrows, void *stream, double *row_device);
+int iwb_reduce_chains_async(iwb_handle *h, const double *gathered_device, int tile_stride, int nfb, void *stream,
+                            double *table_scratch_device, double *row_device);
+
 /* Prepared evaluation: coordinates uploaded and constants derived once, then launched any number
  * of times with NO host<->device traffic (kernel + tile reduction into `table_device` only).
  * This is what a resident-input measurement and a repeated-evaluation driver use.  rho_out, if

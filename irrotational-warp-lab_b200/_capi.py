@@ -114,6 +114,8 @@ SYMBOLS = {
     "iwb_energy3d_slab_async": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.c_void_p, C.c_void_p]),
     "iwb_energy3d_tiles_async": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.c_void_p, C.c_void_p]),
     "iwb_reduce_chains": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(Result)]),
+    "iwb_reduce_table_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "iwb_reduce_chains_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "iwb_plan3d_create": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.POINTER(C.c_void_p)]),
     "iwb_plan3d_run_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "iwb_plan3d_destroy": (C.c_int, [C.c_void_p]),

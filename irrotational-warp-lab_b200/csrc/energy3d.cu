@@ -316,6 +316,30 @@ int iwb_reduce_table(iwb_handle* h, const double* table_device, int nrows, int n
     return IWB_OK;
 }
 
+int iwb_reduce_table_async(iwb_handle* h, const double* table_device, int nrows, void* stream, double* row_device)
+{
+    if (!h || !table_device || !row_device || nrows < 1) return fail(IWB_ERR_INVALID, "iwb_reduce_table_async: bad argument");
+    IWB_CUDA(cudaSetDevice(h->device));
+    k_reduce_rows<<<1, 128, 0, (cudaStream_t)stream>>>(table_device, row_device, nrows);
+    IWB_CUDA(cudaGetLastError());
+    return IWB_OK;
+}
+
+int iwb_reduce_chains_async(iwb_handle* h, const double* gathered_device, int tile_stride, int nfb, void* stream,
+                            double* table_scratch_device, double* row_device)
+{
+    if (!h || !gathered_device || !table_scratch_device || !row_device || nfb < 1)
+        return fail(IWB_ERR_INVALID, "iwb_reduce_chains_async: bad argument");
+    if (!(tile_stride == 1 || tile_stride == 2 || tile_stride == 4 || tile_stride == 8 || tile_stride == 16))
+        return fail(IWB_ERR_INVALID, "iwb_reduce_chains_async: tile_stride must be 1, 2, 4, 8 or 16");
+    IWB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    k_combine_chains<<<nfb, 32 * IWB_TILE_CHAINS, 0, st>>>(gathered_device, table_scratch_device, nfb, tile_stride);
+    k_reduce_rows<<<1, 128, 0, st>>>(table_scratch_device, row_device, nfb);
+    IWB_CUDA(cudaGetLastError());
+    return IWB_OK;
+}
+
 int iwb_debug_spans(long long units, int ctas, int static_pct, int* out, int cap)
 {
     const std::vector<int> b = make_spans(units, ctas, static_pct);

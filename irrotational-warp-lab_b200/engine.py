@@ -160,6 +160,17 @@ class Engine:
                                                 int(nshell), C.c_void_p(int(stream_ptr or 0)), C.byref(r)))
         return self._result_dict(r, nshell)
 
+    def reduce_table_async(self, table_ptr, nrows, row_ptr, stream_ptr=None):
+        """k_reduce_rows into the device row ``row_ptr`` (ROW_WIDTH doubles); no copy, no synchronisation."""
+        _capi.check(self._lib.iwb_reduce_table_async(self._h, C.c_void_p(int(table_ptr)), int(nrows),
+                                                     C.c_void_p(int(stream_ptr or 0)), C.c_void_p(int(row_ptr))))
+
+    def reduce_chains_async(self, gathered_ptr, tile_stride, nfb, scratch_ptr, row_ptr, stream_ptr=None):
+        """Chain tree + row sum into the device row ``row_ptr``; ``scratch_ptr``: [nfb, ROW_WIDTH] doubles; no synchronisation."""
+        _capi.check(self._lib.iwb_reduce_chains_async(self._h, C.c_void_p(int(gathered_ptr)), int(tile_stride), int(nfb),
+                                                      C.c_void_p(int(stream_ptr or 0)), C.c_void_p(int(scratch_ptr)),
+                                                      C.c_void_p(int(row_ptr))))
+
     def plan3d(self, **kw):
         """Prepared evaluation (coordinates resident on the device); see :class:`Plan3D`."""
         return Plan3D(self, **kw)
