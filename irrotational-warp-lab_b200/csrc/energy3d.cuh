@@ -48,6 +48,10 @@
 #ifndef IWB_FLUSH_PACK
 #define IWB_FLUSH_PACK 1    // counts packed two per 32-bit word in the flush butterfly (+0.5 %)
 #endif
+#ifndef IWB_SUM_RHO
+#define IWB_SUM_RHO 0       // prepared experiment (not validated on hardware): tally rho and multiply by dV at the flush
+                            // (one DMUL per point less; energies move in the last bits, inside the 1e-10 bar)
+#endif
 #ifndef IWB_OC_UNROLL
 #define IWB_OC_UNROLL 1     // both rows of the O + C loop unrolled: no loop overhead, row b's loads overlap row a's tally (+0.9 %)
 #endif
@@ -428,8 +432,12 @@ k_energy3d(const __grid_constant__ K3Params P)
                         if (cf0 & 16u) dst[0] = rho2[0];
                         if (cf1 & 16u) dst[32] = rho2[1];
                     }
+#if IWB_SUM_RHO
+                    tally2(rho2, yyj, xxi);        // sums of rho; the flush multiplies by dV (sign(e) == sign(rho): dV > 0)
+#else
                     const double e2[2] = {rho2[0] * P.dV, rho2[1] * P.dV};
                     tally2(e2, yyj, xxi);
+#endif
                 }
                 if (doC && jr >= py_lo && jr <= py_hi) {
                     const unsigned Ah = A + o_ph, Aw = A + o_w;
@@ -563,15 +571,25 @@ k_energy3d(const __grid_constant__ K3Params P)
             constexpr int NV = 6 + 3 * NSH;    // values actually reduced
             double vals[NV];
             // E+ = (sum + sum|.|)/2 and E- = (sum - sum|.|)/2, per thread (halving is exact)
+#if IWB_SUM_RHO
+            const double half_dV = 0.5 * P.dV;
+            vals[0] = (acc_sum + acc_abs) * half_dV; vals[1] = (acc_sum - acc_abs) * half_dV;
+#else
             vals[0] = (acc_sum + acc_abs) * 0.5; vals[1] = (acc_sum - acc_abs) * 0.5;
+#endif
             vals[2] = __longlong_as_double((long long)((cnt3 >> 8) & 0xff));
             vals[3] = __longlong_as_double((long long)(cnt3 & 0xff));
             vals[4] = __longlong_as_double((long long)((cnt3 >> 16) & 0xff));   // zeros + masked columns (corrected below)
             vals[5] = __longlong_as_double(0LL);      // cnt_nan: derived by the host from the other three
 #pragma unroll
             for (int s = 0; s < NSH; ++s) {
+#if IWB_SUM_RHO
+                vals[6 + s] = (sh_sum[s] + sh_abs[s]) * half_dV;
+                vals[6 + NSH + s] = (sh_sum[s] - sh_abs[s]) * half_dV;
+#else
                 vals[6 + s] = (sh_sum[s] + sh_abs[s]) * 0.5;
                 vals[6 + NSH + s] = (sh_sum[s] - sh_abs[s]) * 0.5;
+#endif
                 vals[6 + 2 * NSH + s] = __longlong_as_double((long long)sh_cnt[s]);
             }
 #if IWB_FLUSH_PACK
