@@ -193,6 +193,7 @@ def main(argv=None):
     import torch.distributed as dist
 
     from irrotational_warp_lab_b200 import backend, distributed, sharding
+    from irrotational_warp_lab_b200 import _capi
     from irrotational_warp_lab_b200._capi import ROW_WIDTH, TILE_CHAINS
     from irrotational_warp_lab_b200.engine import get_engine
 
@@ -368,8 +369,7 @@ def main(argv=None):
         # coordinates in; per-(flush block, tile) partial rows out (36 x 60 tiles of the default 40 x 64 geometry, 62 columns
         # in the tiles at the k faces);
         # they are consumed by k_reduce_tiles and usually never leave L2
-        ntk = 1 if n <= 64 else (2 if n <= 124 else 2 + -(-(n - 124) // 60))     # tiles_k (csrc/energy3d.cuh)
-        ntiles = -(-n // 36) * ntk
+        ntiles = _capi.load().iwb_debug_tiles_j(n, None, 0) * _capi.load().iwb_debug_tiles_k(n, None, 0)
         alg_bytes = 8.0 * (2 * n + n + n) + 8.0 * ROW_WIDTH * (r1 - r0) * ntiles / (world if tiles is not None else 1)
         line = {
             "metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": steps, "warmup": warmup,

@@ -253,12 +253,21 @@ int iwb_selftest_constdiv(iwb_handle *h, double divisor, uint64_t count, uint64_
  * the number of tiles (boundaries = tiles + 1), writing at most `cap` ints. */
 int iwb_debug_spans(long long units, int ctas, int static_pct, int *out, int cap);
 int iwb_debug_tiles_k(int n, int *out, int cap);
+/* the same for the rows (j) of the default 40-row region: 36 output rows per interior tile, 38 in the tiles at the j faces */
+int iwb_debug_tiles_j(int n, int *out, int cap);
 
 /* Test hook: the branch-free division / square-root sequences of the exact kernels against the built-in
  * IEEE operators on `count` pseudo-random operand pairs (wide_exponents != 0 also exercises the range
  * check that routes exceptional operands to the built-in sequence; those pairs are counted in *skipped). */
 int iwb_selftest_divsqrt(iwb_handle *h, uint64_t count, uint64_t seed, int wide_exponents, uint64_t *mismatches_div,
                          uint64_t *mismatches_sqrt, uint64_t *skipped);
+
+/* Test hook: the branch-free phi evaluation of the exact 3D kernel (square root, the two divisions with reciprocal seeds
+ * taken from the square root's 1/sqrt, the wall flavour with exp / log1p) against the plain IEEE operators on `count`
+ * pseudo-random points whose coordinates are log-uniform in +-[coord_lo, coord_hi); *mismatches counts results that
+ * differ in any bit, *wall_points (may be NULL) the points that took the exp / log1p flavour. */
+int iwb_selftest_phi(iwb_handle *h, double rho, double sigma, double v, double eps, double coord_lo, double coord_hi,
+                     uint64_t count, uint64_t seed, uint64_t *mismatches, uint64_t *wall_points);
 
 #ifdef __cplusplus
 }

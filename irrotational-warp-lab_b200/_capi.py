@@ -128,8 +128,11 @@ SYMBOLS = {
     "iwb_measure_fma_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "iwb_selftest_divsqrt": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64),
                                        C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "iwb_selftest_phi": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                   C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "iwb_debug_spans": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "iwb_debug_tiles_k": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int]),
+    "iwb_debug_tiles_j": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int]),
     "iwb_selftest_constdiv": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
 }
 

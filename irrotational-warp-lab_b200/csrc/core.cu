@@ -86,8 +86,20 @@ bool phi_fast_path_is_safe(const double* const coords[3], const int n[3], double
     }
     const double K = (2.0 * sigma) * sinh_rs;
     if (!isfinite(K) || K == 0.0 || !zero_or_in_range(fabs(K), -150, 150)) ok = false;
+    // smallest non-zero r of the grid >= smallest non-zero |coordinate|
+    double cmin = INFINITY;
+    for (int a = 0; a < 3; ++a)
+        for (int i = 0; i < n[a]; ++i)
+            if (coords[a][i] != 0.0 && fabs(coords[a][i]) < cmin) cmin = fabs(coords[a][i]);
+    // the reference zeroes g where |t1| <= 1e-12, t1 = (2 r sigma) sinh(rho sigma) (potential.py:73-77); the branch-free
+    // flavour has no such test, so every non-zero r must be clear of the threshold (tiny sigma: K ~ 1e-13 and below)
+    if (isfinite(cmin) && !(fabs(K) * cmin > 1.0000001e-12)) ok = false;
+    // reciprocal seed of x / (r + eps) from 1/r (div_seeded): (eps / r)^2 < 2^-56
+    if (isfinite(cmin) && !(eps <= cmin * 0x1p-28)) ok = false;
     if (!isfinite(cosh_rs) || !isfinite(rho) || !isfinite(sigma) || !isfinite(v)) ok = false;
     if (!(eps >= 0.0) || !(eps <= 1.0)) ok = false;
+    if (!(sigma > 0.0) || !(rho >= 0.0)) ok = false;          // |sigma (r + rho)| >= |sigma (r - rho)|: one wall test per point
+    if (float32_grid && !((float)sigma > 0.0f)) ok = false;
     if (float32_grid && !(fabs(rho) <= 0x1p40 && fabs(sigma) <= 0x1p40 && fabs(v) <= 0x1p40 && (eps == 0.0 || eps >= 0x1p-100))) ok = false;
     if (!(fabs(rho) <= 0x1p200) || !(fabs(sigma) <= 0x1p200) || !(fabs(v) <= 0x1p200)) ok = false;
     return ok;
@@ -99,15 +111,24 @@ PhiConst make_phi_const(double rho, double sigma, double v, double eps, double s
     c.prechecked = 0;
     c.sigma = sigma; c.sigma2 = 2.0 * sigma; c.rho = rho; c.v = v; c.eps = eps;
     c.S = sinh_rs; c.C = cosh_rs;
+    c.rK = (double)(1.0L / ((long double)c.sigma2 * (long double)sinh_rs));
     c.sigf = (float)sigma; c.sig2f = 2.0f * (float)sigma; c.rhof = (float)rho; c.vf = (float)v; c.epsf = (float)eps;
     return c;
 }
 
 // ---- register-resident FMA throughput (roofline denominator) -------------------------------------
+// One CTA of 16 warps per SM, 8 independent chains per thread: 4 warps x 8 chains per scheduler against a dependent-issue
+// latency of 8 cycles (DFMA) / 4 cycles (FFMA), so the pipe never waits for an operand.  Thread 0 of every CTA reports
+// the clock64 cycles of its loop: cycles / event time is the SM clock the benchmark actually ran at, and
+// FMAs / cycles the pipe occupancy (1.000 = one warp instruction every 2 cycles per scheduler for FP64).
+// (The round-1 version -- 8 CTAs of 256 threads per SM, 4.7 ms -- reached 92 % of the pipe under ncu,
+// profiles/r2_fma_peak_ncu_summary.txt; scripts/probes/fp64_probe.cu is the latency / throughput study.)
 template <typename T>
-__global__ void __launch_bounds__(256) k_fma_peak(T* sink, int iters, T a, T b)
+__global__ void __launch_bounds__(512) k_fma_peak(T* sink, long long* cycles, int iters, T a, T b)
 {
     T v0 = (T)threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    __syncthreads();
+    const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -115,8 +136,10 @@ __global__ void __launch_bounds__(256) k_fma_peak(T* sink, int iters, T a, T b)
             v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
         }
     }
+    const long long t1 = clock64();
     T r = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
     if (r == (T)123456789) sink[0] = r;   // never true; keeps the chain alive
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
 // ---- constant-divisor division self-test -----------------------------------------------------------
@@ -268,26 +291,33 @@ int iwb_measure_fma_peak(iwb_handle* h, int use_fp32, double* tflops, double* sm
     if (!h || !tflops) return fail(IWB_ERR_INVALID, "iwb_measure_fma_peak: null argument");
     IWB_CUDA(cudaSetDevice(h->device));
     Scratch& c = h->scr[0];
-    IWB_CUDA(c.out.reserve(ROW_BYTES_MIN));
-    const int grid = h->sm_count * 8, block = 256, iters = 4096;
-    double best_ms = 1e30;
-    for (int rep = 0; rep < 6; ++rep) {
+    IWB_CUDA(c.out.reserve(ROW_BYTES_MIN + 8 * 1024));
+    double* sink = (double*)c.out.p;
+    long long* cyc = (long long*)((char*)c.out.p + ROW_BYTES_MIN);
+    const int grid = h->sm_count < 1024 ? h->sm_count : 1024, block = 512, iters = use_fp32 ? 60000 : 30000;
+    double best_ms = 1e30, best_cycles = 0.0;
+    long long hc[1024];
+    for (int rep = 0; rep < 5; ++rep) {
         IWB_CUDA(cudaEventRecord(c.ev0, c.stream));
-        if (use_fp32) k_fma_peak<float><<<grid, block, 0, c.stream>>>((float*)c.out.p, iters, 1.0000001f, 1e-9f);
-        else k_fma_peak<double><<<grid, block, 0, c.stream>>>((double*)c.out.p, iters, 1.0000000001, 1e-12);
+        if (use_fp32) k_fma_peak<float><<<grid, block, 0, c.stream>>>((float*)sink, cyc, iters, 1.0000001f, 1e-9f);
+        else k_fma_peak<double><<<grid, block, 0, c.stream>>>(sink, cyc, iters, 1.0000000001, 1e-12);
         IWB_CUDA(cudaEventRecord(c.ev1, c.stream));
-        IWB_CUDA(cudaEventSynchronize(c.ev1));
+        IWB_CUDA(cudaMemcpyAsync(hc, cyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost, c.stream));
+        IWB_CUDA(cudaStreamSynchronize(c.stream));
         IWB_CUDA(cudaGetLastError());
         float ms = 0;
         IWB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
-        if (rep > 0 && ms < best_ms) best_ms = ms;
+        if (rep > 0 && ms < best_ms) {
+            best_ms = ms;
+            double mx = 0.0;
+            for (int q = 0; q < grid; ++q) mx = hc[q] > mx ? (double)hc[q] : mx;
+            best_cycles = mx;
+        }
     }
     const double fmas = (double)grid * block * (double)iters * 64.0;
     *tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
-    if (sm_mhz_effective) {
-        const double lanes = use_fp32 ? 128.0 : 64.0;
-        *sm_mhz_effective = fmas / (best_ms * 1e-3) / (h->sm_count * lanes) / 1e6;
-    }
+    // the clock the SMs ran at: loop cycles of the slowest CTA over the event time (which adds the launch, ~0.1 %)
+    if (sm_mhz_effective) *sm_mhz_effective = best_cycles / (best_ms * 1e-3) / 1e6;
     return IWB_OK;
 }
 

@@ -44,6 +44,12 @@ static int validate(const iwb_params3d* p)
         return fail(IWB_ERR_INVALID, "energy3d: i_begin must be a multiple of IWB_FLUSH_PLANES");
     if (p->nshell < 0 || p->nshell > IWB_MAX_SHELLS) return fail(IWB_ERR_INVALID, "energy3d: nshell out of range");
     if (!(p->dx > 0.0) || !(p->dy > 0.0) || !(p->dz > 0.0)) return fail(IWB_ERR_INVALID, "energy3d: spacings must be > 0");
+    {
+        // the kernel tallies rho and scales by dV at the flush; its exact zero / sign classification of rho * dV assumes
+        // that only a rho below 2^-511 can underflow in that product
+        const double dV = (p->dx * p->dy) * p->dz;
+        if (!(dV >= 0x1p-400 && dV <= 0x1p400)) return fail(IWB_ERR_INVALID, "energy3d: dx*dy*dz outside [2^-400, 2^400]");
+    }
     const int ts = p->tile_stride;
     if (!(ts == 0 || ts == 1 || ts == 2 || ts == 4 || ts == 8 || ts == 16))
         return fail(IWB_ERR_INVALID, "energy3d: tile_stride must be 0, 1, 2, 4, 8 or 16");
@@ -97,7 +103,7 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
     const K3Config cfg = kConfigs[cfg_id];
 
     // work spans of the fused kernel (see k_energy3d), staged behind the coordinates
-    const int ntj_ = (n1 + (cfg.rj - 4) - 1) / (cfg.rj - 4), ntk_ = tiles_k(n2);
+    const int ntj_ = tiles_j(n1, cfg.rj), ntk_ = tiles_k(n2);
     const int tstride = p->tile_stride > 1 ? p->tile_stride : 1, tfirst = p->tile_stride > 1 ? p->tile_first : 0;
     const int ntiles_local = (ntj_ * ntk_ - tfirst + tstride - 1) / tstride;      // may be 0 on a tiny grid
     // share of the units in the large spans: 80 % when the launch covers the whole of axis 0 (every CTA's span then
@@ -129,7 +135,7 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
     memset(&P, 0, sizeof(P));
     P.n0 = n0; P.n1 = n1; P.n2 = n2;
     P.i_begin = p->i_begin; P.i_end = p->i_end;
-    P.ntj = (n1 + (cfg.rj - 4) - 1) / (cfg.rj - 4);
+    P.ntj = tiles_j(n1, cfg.rj);
     P.ntk = tiles_k(n2);
     const int ntiles = P.ntj * P.ntk;
     const int planes = p->i_end - p->i_begin;
@@ -248,6 +254,36 @@ static int enqueue_full(iwb_handle* h, Scratch& c, const iwb_params3d* p)
     return IWB_OK;
 }
 
+// ---- phi self-test: the branch-free flavour against the plain operators on random points -------------------------
+// (lives here because this translation unit is compiled with -fmad=false like the kernels it checks)
+__global__ void k_selftest_phi(PhiConst pc, double lo, double hi, uint64_t count, uint64_t seed, unsigned long long* out)
+{
+    const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0, wall = 0;
+    for (uint64_t n = tid; n < count; n += stride) {
+        double c[3];
+        for (int k = 0; k < 3; ++k) {
+            uint64_t z = seed + 0x9E3779B97F4A7C15ull * (3 * n + k + 1);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            z ^= z >> 31;
+            const double u = (double)(z >> 11) * 0x1p-53;              // [0, 1)
+            // log-uniform magnitude in [lo, hi), random sign
+            const double mag = lo * exp(u * log(hi / lo));
+            c[k] = (z & 1) ? -mag : mag;
+        }
+        const double s[1] = {(c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]};
+        double f[1];
+        phi_exact_f64<1, true>(s, c[0], pc, f);
+        const double ref = phi_point_f64_ref(s[0], c[0], pc.sigma, pc.sigma2, pc.rho, pc.v, pc.eps, pc.S, pc.C);
+        if (__double_as_longlong(f[0]) != __double_as_longlong(ref)) ++bad;
+        const double r = sqrt(s[0]);
+        if (fabs(pc.sigma * (r - pc.rho)) < LAE_SKIP_F64) ++wall;
+    }
+    if (bad) atomicAdd(out, bad);
+    if (wall) atomicAdd(out + 1, wall);
+}
+
 }  // namespace iwb
 
 struct iwb_plan3d {
@@ -340,6 +376,37 @@ int iwb_reduce_chains_async(iwb_handle* h, const double* gathered_device, int ti
     return IWB_OK;
 }
 
+int iwb_selftest_phi(iwb_handle* h, double rho, double sigma, double v, double eps, double coord_lo, double coord_hi,
+                     uint64_t count, uint64_t seed, uint64_t* mismatches, uint64_t* wall_points)
+{
+    if (!h || !mismatches) return fail(IWB_ERR_INVALID, "iwb_selftest_phi: null argument");
+    if (!(coord_lo > 0.0) || !(coord_hi > coord_lo)) return fail(IWB_ERR_INVALID, "iwb_selftest_phi: need 0 < coord_lo < coord_hi");
+    const double sinh_rs = sinh(rho * sigma), cosh_rs = cosh(rho * sigma);
+    PhiConst pc = make_phi_const(rho, sigma, v, eps, sinh_rs, cosh_rs);
+    {   // the host's operand-range proof on the two extreme coordinates (every |coordinate| lies between them)
+        const double ax[2] = {coord_lo, coord_hi};
+        const double* const coords[3] = {ax, ax, ax};
+        const int nn[3] = {2, 2, 2};
+        int zero_index[3];
+        if (!phi_fast_path_is_safe(coords, nn, rho, sigma, v, eps, sinh_rs, cosh_rs, zero_index, false))
+            return fail(IWB_ERR_INVALID, "iwb_selftest_phi: these parameters fail the operand-range proof (the engine "
+                                         "would use the reference flavour throughout)");
+    }
+    pc.prechecked = 1;
+    IWB_CUDA(cudaSetDevice(h->device));
+    Scratch& c = h->scr[0];
+    IWB_CUDA(c.out.reserve(ROW_BYTES_MIN));
+    IWB_CUDA(cudaMemsetAsync(c.out.p, 0, 16, c.stream));
+    k_selftest_phi<<<h->sm_count * 8, 256, 0, c.stream>>>(pc, coord_lo, coord_hi, count, seed, (unsigned long long*)c.out.p);
+    IWB_CUDA(cudaGetLastError());
+    unsigned long long res[2] = {0, 0};
+    IWB_CUDA(cudaMemcpyAsync(res, c.out.p, 16, cudaMemcpyDeviceToHost, c.stream));
+    IWB_CUDA(cudaStreamSynchronize(c.stream));
+    *mismatches = res[0];
+    if (wall_points) *wall_points = res[1];
+    return IWB_OK;
+}
+
 int iwb_debug_spans(long long units, int ctas, int static_pct, int* out, int cap)
 {
     const std::vector<int> b = make_spans(units, ctas, static_pct);
@@ -353,6 +420,15 @@ int iwb_debug_tiles_k(int n, int* out, int cap)
     const int nt = tiles_k(n);
     for (int t = 0; t <= nt && t < cap; ++t)
         if (out) out[t] = tile_begin_k(t, nt, n);
+    return nt;
+}
+
+int iwb_debug_tiles_j(int n, int* out, int cap)
+{
+    const int rj = kConfigs[1].rj;       // the default geometry (region of 40 rows)
+    const int nt = tiles_j(n, rj);
+    for (int t = 0; t <= nt && t < cap; ++t)
+        if (out) out[t] = tile_begin_j(t, nt, n, rj);
     return nt;
 }
 
@@ -401,6 +477,8 @@ int iwb_radial_profile3d(iwb_handle* h, const iwb_params3d* p, const iwb_profile
     const int nb = prof->n_bins;
     if (nb < 1 || nb > PROF_MAX_BINS) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: n_bins must be in [1, 256]");
     if (!prof->edges || !prof->sum || !prof->count) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: edges / sum / count are NULL");
+    for (int q = 0; q <= nb; ++q)
+        if (!isfinite(prof->edges[q])) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: edges must be finite");
     for (int q = 0; q < nb; ++q)
         if (!(prof->edges[q + 1] > prof->edges[q])) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: edges must be strictly increasing");
     auto t0 = std::chrono::steady_clock::now();
@@ -447,7 +525,7 @@ int iwb_radial_profile3d(iwb_handle* h, const iwb_params3d* p, const iwb_profile
         R.xx = L.P.xx; R.yy = L.P.yy; R.zz = L.P.zz;
         R.edges = dprof;
         R.n1 = p->n1; R.n2 = p->n2; R.i_begin = q.i_begin; R.i_end = q.i_end; R.nb = nb; R.dtype = p->dtype;
-        R.inv_width = (double)nb / prof->edges[nb];
+        R.inv_width = (double)nb / (prof->edges[nb] - prof->edges[0]);     // finite and > 0 (an overflowing span gives 0)
         R.part_sum = dprof + off_psum;
         R.part_cnt = (long long*)(dprof + off_pcnt);
         k_radial_hist<<<dim3(PROF_SUB, L.fb1 - L.fb0), PROF_NW * 32, 0, st>>>(R);

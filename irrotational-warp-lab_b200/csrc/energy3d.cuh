@@ -48,15 +48,33 @@
 #ifndef IWB_FLUSH_PACK
 #define IWB_FLUSH_PACK 1    // counts packed two per 32-bit word in the flush butterfly (+0.5 %)
 #endif
+
 #ifndef IWB_SUM_RHO
-#define IWB_SUM_RHO 0       // prepared experiment (not validated on hardware): tally rho and multiply by dV at the flush
-                            // (one DMUL per point less; energies move in the last bits, inside the 1e-10 bar)
+#define IWB_SUM_RHO 1       // tally rho and multiply by dV at the flush: one DMUL per point less (+0.25 % on B200); the sums
+                            // move in the last bit (bar: 1e-10), the signs are those of rho (dV > 0); needs IWB_TALLY == 2
+                            // for exact zero counts when rho * dV underflows
 #endif
 #ifndef IWB_OC_UNROLL
 #define IWB_OC_UNROLL 1     // both rows of the O + C loop unrolled: no loop overhead, row b's loads overlap row a's tally (+0.9 %)
 #endif
 #ifndef IWB_P4
 #define IWB_P4 1       // task P evaluates both rows of a warp at once: four independent phi evaluations per thread
+#endif
+#ifndef IWB_JFACE
+#define IWB_JFACE 1    // tiles at the two j faces hold RJ - 2 output rows (no halo beyond the face), as the k-face tiles hold
+                       // RK - 2 columns: n = 256 is 7 instead of 8 tile rows, n = 400 11 instead of 12
+#endif
+#ifndef IWB_TALLY
+#define IWB_TALLY 2    // 1: round-1 tally (two FP64 compares per point, per-row shell test from sxy + zzmin)
+                       // 2: integer sign count with a rare path for zero / NaN / inf, per-tile row tables for the shell
+                       //    tests (skip / fully inside / mixed), pair sums
+#endif
+#if !IWB_FLUSH_PACK && IWB_TALLY == 2
+#error "IWB_TALLY == 2 derives the positive count in the packed flush only"
+#endif
+#ifndef IWB_NBSYNC
+#define IWB_NBSYNC 0   // 1: the march synchronises each warp with its two row neighbours only (progress counters in shared
+                       // memory) instead of one CTA-wide mbarrier phase per plane; 2: same with a relaxed flag store
 #endif
 #ifndef IWB_DBG
 #define IWB_DBG 0      // development only: 1 = skip task O, 2 = skip the phi evaluation, 3 = both
@@ -68,7 +86,9 @@ constexpr int RK = 64;              // region columns (k): two per lane
 constexpr int TK_MAX = RK - 4;      // tile columns
 constexpr int ROW = IWB_ROW_WIDTH;  // doubles per partial row
 constexpr int FLUSH = IWB_FLUSH_PLANES;
-constexpr int SMEM_PAD = 8;         // guard doubles before and after the planes (lane 0 / lane 31 reads of idx -+ 1)
+constexpr int SMEM_PAD = 8;         // guard doubles after the planes (lane 31 reads idx + 1)
+constexpr int SMEM_PAD_FRONT = IWB_JFACE ? RK + 8 : 8;   // guard before the planes: lane 0 reads idx - 1, and the central formula
+                                    // of a face row reads the row below region row 0 before the one-sided formula overrides it
 constexpr int NPLANES = 11;
 constexpr int NEDGE = 18;           // one-sided coefficients a0 b0 c0 a1 b1 c1 of the three axes (shared-memory copy)
 
@@ -98,22 +118,42 @@ struct K3Params {
 
 __host__ __device__ inline int tile_begin(int t, int nt, int n) { return (int)(((long long)t * n) / nt); }
 
-// Columns (k): an interior tile holds at most TK_MAX = RK - 4 output columns (2-column halo on either side), but the
-// tile at a global face needs no halo beyond the face and holds RK - 2 -- a single tile RK.  n = 1024 is 17 tiles
-// (2 x 62 + 15 x 60) instead of 18.  tiles_k: number of tiles; tile_begin_k: first column of tile t (t = nt: n), the
-// slack spread evenly over the tiles.
-__host__ __device__ inline int tiles_k(int n)
+// Tiles along one axis of the (j, k) plane for a region of R points: an interior tile holds at most R - 4 output points
+// (2-point halo on either side), but the tile at a global face needs no halo beyond the face and holds R - 2 -- a single
+// tile R.  n = 1024 columns are 17 tiles (2 x 62 + 15 x 60) instead of 18.  tiles_1d: number of tiles; tile_begin_1d:
+// first point of tile t (t = nt: n), the slack spread evenly over the tiles.
+__host__ __device__ inline int tiles_1d(int n, int R)
 {
-    if (n <= RK) return 1;
-    if (n <= 2 * (RK - 2)) return 2;
-    return 2 + (n - 2 * (RK - 2) + TK_MAX - 1) / TK_MAX;
+    if (n <= R) return 1;
+    if (n <= 2 * (R - 2)) return 2;
+    return 2 + (n - 2 * (R - 2) + (R - 4) - 1) / (R - 4);
 }
-__host__ __device__ inline int tile_begin_k(int t, int nt, int n)
+__host__ __device__ inline int tile_begin_1d(int t, int nt, int n, int R)
 {
     if (t <= 0) return 0;
     if (t >= nt) return n;
-    const int slack = 2 * (RK - 2) + (nt - 2) * TK_MAX - n;
-    return (RK - 2) + (t - 1) * TK_MAX - (int)(((long long)t * slack) / nt);
+    const int slack = 2 * (R - 2) + (nt - 2) * (R - 4) - n;
+    return (R - 2) + (t - 1) * (R - 4) - (int)(((long long)t * slack) / nt);
+}
+__host__ __device__ inline int tiles_k(int n) { return tiles_1d(n, RK); }
+__host__ __device__ inline int tile_begin_k(int t, int nt, int n) { return tile_begin_1d(t, nt, n, RK); }
+// rows (j) of a region of RJ rows
+__host__ __device__ inline int tiles_j(int n, int RJ)
+{
+#if IWB_JFACE
+    return tiles_1d(n, RJ);
+#else
+    return (n + (RJ - 4) - 1) / (RJ - 4);
+#endif
+}
+__host__ __device__ inline int tile_begin_j(int t, int nt, int n, int RJ)
+{
+#if IWB_JFACE
+    return tile_begin_1d(t, nt, n, RJ);
+#else
+    (void)RJ;
+    return tile_begin(t, nt, n);
+#endif
 }
 
 template <int RJ, int NW>
@@ -122,7 +162,8 @@ struct Geo {
     static constexpr int TJ_MAX = RJ - 4;
     static constexpr int NT = NW * 32;
     static constexpr int SCRATCH = NW * ROW;     // block-reduction scratch (doubles)
-    static constexpr size_t SMEM_BYTES = (size_t(NPLANES) * PLANE + 2 * SMEM_PAD + RJ + SCRATCH + NEDGE) * sizeof(double);
+    static constexpr int NROWTAB = (IWB_TALLY == 2) ? 4 : 1;     // per-row tables: y*y [, x*x limits: outside all shells, inside shell 0, 1]
+    static constexpr size_t SMEM_BYTES = (size_t(NPLANES) * PLANE + SMEM_PAD_FRONT + SMEM_PAD + NROWTAB * RJ + SCRATCH + NEDGE) * sizeof(double);
 };
 
 template <int DT, int NSH, int RJ, int NW, bool EMIT, int MINB = 1, int MODE = 0>
@@ -133,12 +174,12 @@ k_energy3d(const __grid_constant__ K3Params P)
     constexpr int PLANE = G::PLANE;
     constexpr int NSHA = NSH > 0 ? NSH : 1;
     extern __shared__ double smem_raw[];
-    double* const phi_ring = smem_raw + SMEM_PAD;          // 3 planes
+    double* const phi_ring = smem_raw + SMEM_PAD_FRONT;    // 3 planes
     double* const px_ring = phi_ring + 3 * PLANE;          // 4 planes
     double* const py_buf = phi_ring + 7 * PLANE;           // 2 planes
     double* const pz_buf = phi_ring + 9 * PLANE;           // 2 planes
-    double* const yy_s = phi_ring + NPLANES * PLANE + SMEM_PAD;   // [RJ] y*y of the region rows
-    double* const scratch = yy_s + RJ;                     // [NW][ROW]
+    double* const yy_s = phi_ring + NPLANES * PLANE + SMEM_PAD;   // [RJ] y*y of the region rows [+ 3 x RJ shell-test limits]
+    double* const scratch = yy_s + G::NROWTAB * RJ;        // [NW][ROW]
     // One-sided (global face) coefficients live in shared memory: only the edge flavours of the tasks read them,
     // and as kernel parameters they would occupy 36 uniform registers that the interior loops need for their constants.
     double* const ec_s = scratch + G::SCRATCH;             // [3][6]: x, y, z -> a0 b0 c0 a1 b1 c1
@@ -170,6 +211,50 @@ k_energy3d(const __grid_constant__ K3Params P)
         ec_s[threadIdx.x] = (&P.cx.h2)[8 * axis + 2 + q];
     }
     __syncthreads();
+#if IWB_NBSYNC
+    // Neighbour synchronisation of the march.  Every cross-warp dependency of a step runs between ROW neighbours: O(i)
+    // reads phi_x(i), phi_y(i) of the rows j -+ 1, C(i+1) reads phi(i+1) of the rows j -+ 1; columns k -+ 1 belong to the
+    // warp itself, the x direction to the thread itself.  Warp w owns the rows w and w + NW, so its neighbours are the
+    // warps w -+ 1 (cyclically: row NW - 1 belongs to warp NW - 1, row NW to warp 0).  The hazards (read-after-write on
+    // phi_x / phi_y / phi, write-after-read on the phi_y / phi_z buffer and the phi / phi_x ring slots that step i
+    // recycles) all reduce to ONE rule: warp w may start O(i) + C(i+1) once both neighbours have finished
+    // O(i-1) + C(i); task P(i+3) writes own columns only and needs nothing more.  s_prog[w] counts the steps whose
+    // O + C warp w has finished (monotonic over the kernel); neighbours differ by at most one step, distant warps may
+    // drift further, so one slow warp (wall rows, a late wake-up) no longer stops the other nineteen.
+    // s_prog[1 + w] is warp w's counter; entry 0 mirrors warp NW - 1 and entry NW + 1 mirrors warp 0, so that every
+    // warp finds its neighbours at -+ 4 bytes of its own entry (one address register).
+    __shared__ unsigned s_prog[NW + 2];
+    static_assert(RJ == 2 * NW, "row neighbours are the warps w -+ 1 only when every warp owns the rows w and w + NW");
+    if (threadIdx.x < NW + 2) s_prog[threadIdx.x] = 0u;
+    __syncthreads();
+    unsigned nb_step = 0;                                  // march steps completed by this warp (same on all lanes)
+    const unsigned prog_me = keep_u32((unsigned)__cvta_generic_to_shared(&s_prog[1 + ty]));
+    auto step_wait = [&]() {       // before O(i+1) + C(i+2): both neighbours have arrived at this step (and so at every earlier one)
+        for (;;) {
+            unsigned a, b;
+            asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1+-4];" : "=r"(a) : "r"(prog_me) : "memory");
+            asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1+4];" : "=r"(b) : "r"(prog_me) : "memory");
+            // (the vote makes the exit warp-uniform: the code after the loop stays on the uniform datapath)
+            if (__all_sync(0xffffffffu, (int)(a - nb_step) >= 0 && (int)(b - nb_step) >= 0)) break;
+            __nanosleep(IWB_BARRIER_BACKOFF_NS);
+        }
+    };
+    auto step_arrive = [&]() {     // after O(i) + C(i+1)
+        __syncwarp();
+        ++nb_step;
+        if (tx == 0) {
+#if IWB_NBSYNC == 2
+            asm volatile("st.volatile.shared::cta.u32 [%0], %1;" ::"r"(prog_me), "r"(nb_step) : "memory");
+            if (ty == 0) asm volatile("st.volatile.shared::cta.u32 [%0+%2], %1;" ::"r"(prog_me), "r"(nb_step), "n"(4 * NW) : "memory");
+            if (ty == NW - 1) asm volatile("st.volatile.shared::cta.u32 [%0+%2], %1;" ::"r"(prog_me), "r"(nb_step), "n"(-4 * NW) : "memory");
+#else
+            asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(prog_me), "r"(nb_step) : "memory");
+            if (ty == 0) asm volatile("st.relaxed.cta.shared::cta.u32 [%0+%2], %1;" ::"r"(prog_me), "r"(nb_step), "n"(4 * NW) : "memory");
+            if (ty == NW - 1) asm volatile("st.relaxed.cta.shared::cta.u32 [%0+%2], %1;" ::"r"(prog_me), "r"(nb_step), "n"(-4 * NW) : "memory");
+#endif
+        }
+    };
+#else
     auto step_arrive = [&]() { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar_addr) : "memory"); };
     auto step_wait = [&]() {
         unsigned done;
@@ -183,6 +268,7 @@ k_energy3d(const __grid_constant__ K3Params P)
         }
         mbar_parity ^= 1u;
     };
+#endif
     // Work distribution.  A unit is (tile, flush block); units are ordered tile-major, and a SPAN is a contiguous range
     // of units.  A CTA marches through the units of a span without interruption -- the rings stay primed, so only the
     // first unit of a tile within a span pays the 4-plane phi prologue -- and spans are handed out in index order by an
@@ -222,21 +308,23 @@ k_energy3d(const __grid_constant__ K3Params P)
             }
         }
         const int tj = tile / P.ntk, tk = tile - tj * P.ntk;
-        const int j0 = tile_begin(tj, P.ntj, P.n1), Tj = tile_begin(tj + 1, P.ntj, P.n1) - j0;
+        const int j0 = tile_begin_j(tj, P.ntj, P.n1, RJ), Tj = tile_begin_j(tj + 1, P.ntj, P.n1, RJ) - j0;
         const int k0 = tile_begin_k(tk, P.ntk, P.n2), Tk = tile_begin_k(tk + 1, P.ntk, P.n2) - k0;
         const int hl = (k0 == 0) ? 0 : 2;           // halo columns on the low side: region column c is k = k0 - hl + c
         const int i0 = P.i_begin + fblk0 * FLUSH;
         const int i1 = min(P.i_end, P.i_begin + fblk1 * FLUSH);
 
-        // region rows [jr_lo, jr_hi] exist in the grid; j == 0 is region row 2 of a low-edge tile,
-        // j == n1-1 is region row Tj+1 of a high-edge tile
+        // Region row jr is j = j0 - hj + jr (hj halo rows on the low side); the output rows are [o_lo, o_hi]; the rows
+        // [jr_lo, jr_hi] exist in the grid (j == 0 is region row o_lo of a low-face tile, j == n1-1 row o_hi of a high-face one)
         const bool t_jlo = (j0 == 0), t_jhi = (j0 + Tj == P.n1);
         const bool t_kedge = (k0 == 0) || (k0 + Tk == P.n2);
         const bool tile_edge = t_jlo || t_jhi || t_kedge;
-        const int jr_lo = t_jlo ? 2 : 0, jr_hi = t_jhi ? Tj + 1 : Tj + 3;
-        const int py_lo = max(jr_lo, 1), py_hi = min(jr_hi, Tj + 2);
+        const int hj = (IWB_JFACE && t_jlo) ? 0 : 2;
+        const int o_lo = hj, o_hi = hj + Tj - 1;
+        const int jr_lo = t_jlo ? o_lo : 0, jr_hi = t_jhi ? o_hi : o_hi + 2;
+        const int py_lo = max(jr_lo, o_lo - 1), py_hi = min(jr_hi, o_hi + 1);
 
-        if (threadIdx.x < RJ) yy_s[threadIdx.x] = P.yy[min(max(j0 - 2 + (int)threadIdx.x, 0), P.n1 - 1)];
+        if (threadIdx.x < RJ) yy_s[threadIdx.x] = P.yy[min(max(j0 - hj + (int)threadIdx.x, 0), P.n1 - 1)];
 
         // this lane's two columns
         double zz0, zz1;
@@ -259,6 +347,34 @@ k_energy3d(const __grid_constant__ K3Params P)
             for (int off = 16; off > 0; off >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, off));
             zzmin_s = m;
         }
+#if IWB_TALLY == 2
+        // hi-word OR-masks that make a non-output column look like 1.0 to the special-value test of the tally, and the
+        // number of output columns of this lane
+        const int fx0 = (int)keep_u32((cf0 & 16u) ? 0u : 0x3ff00000u), fx1 = (int)keep_u32((cf1 & 16u) ? 0u : 0x3ff00000u);
+        const int npl = (int)((cf0 >> 4) & 1u) + (int)((cf1 >> 4) & 1u);
+        constexpr int NIN = (NSH >= 1 && NSH <= 2) ? NSH : 0;     // shells with a "row fully inside" table
+        if (NSH > 0) {
+            // Row tables of the shell tests.  s = RN(RN(x*x + y*y) + z*z) is monotone in each term, so for a row (fixed y)
+            // of this tile:  x*x > xout[row]  =>  even the column with the smallest z*z lies outside the largest shell;
+            //                x*x <= xin[s][row]  =>  even the column with the largest z*z lies inside shell s.
+            // The limits are conservative (a relative margin far above the rounding errors of s: float64 2^-40, float32
+            // 2^-18), so a row they leave undecided simply takes the exact per-point comparison.
+            double zzmax = fmax((cf0 & 16u) ? zz0 : -INFINITY, (cf1 & 16u) ? zz1 : -INFINITY);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) zzmax = fmax(zzmax, __shfl_xor_sync(0xffffffffu, zzmax, off));
+            if (threadIdx.x < RJ) {
+                const double yyv = P.yy[min(max(j0 - hj + (int)threadIdx.x, 0), P.n1 - 1)];
+                const double mrg = (DT == IWB_F64) ? 0x1p-40 : 0x1p-18;
+                const double tm = P.shell_thr_max;
+                yy_s[RJ + threadIdx.x] = (tm < 0.0) ? -1.0 : ((tm - yyv) - zzmin_s) + ((tm + yyv) + zzmin_s) * mrg;
+#pragma unroll
+                for (int sh = 0; sh < NIN; ++sh) {
+                    const double th = P.shell_thr[sh];
+                    yy_s[(2 + sh) * RJ + threadIdx.x] = (th < 0.0) ? -1.0 : ((th - yyv) - zzmax) - ((th + yyv) + zzmax) * mrg;
+                }
+            }
+        }
+#endif
 
         // ---- accumulators (registers) -------------------------------------------------
         double acc_sum = 0.0, acc_abs = 0.0;        // sum(e), sum(|e|) over the thread's output points
@@ -281,7 +397,78 @@ k_energy3d(const __grid_constant__ K3Params P)
         // Counts: every point is exactly one of neg / pos / zero / NaN; the first three are counted here in 8-bit
         // fields of one register (<= 64 points per thread and flush interval), NaN is derived by the host.  The zero
         // field also counts the masked non-output columns; the flush subtracts their (known) number.
-        auto tally2 = [&](const double (&e)[2], double yyj, double xxi) {
+#if IWB_TALLY == 2
+        // Pair sums first (e0 + e1, |e0| + |e1|): the main accumulators and every shell the row lies fully inside take the
+        // same two values.  Counts: the sign bit of the masked value counts the negative points; a point whose high word
+        // says zero / denormal / inf / NaN sends its thread through an exact, rare path that counts zeros and NaNs and
+        // takes the sign count back where it does not apply (-0.0, -NaN); positives are derived at the flush.  cnt3
+        // fields: negative | NaN << 8 | zero << 16.
+        auto tally2 = [&](const double (&e)[2], unsigned ya, double xxi) {
+            const int h0 = __double2hiint(e[0]), h1 = __double2hiint(e[1]);
+            const int hm0 = h0 & om0, hm1 = h1 & om1;
+            const double em0 = __hiloint2double(hm0, __double2loint(e[0]) & om0);
+            const double em1 = __hiloint2double(hm1, __double2loint(e[1]) & om1);
+            const double t = em0 + em1, ta = fabs(em0) + fabs(em1);
+            acc_sum += t; acc_abs += ta;
+            cnt3 += (int)((unsigned)hm0 >> 31) + (int)((unsigned)hm1 >> 31);
+            // |value| < 2^-511 (zero, denormal, or so small that value * dV may underflow when rho is tallied) or exponent
+            // all ones (inf, NaN), at an output column: classify exactly what the reference classifies, e = rho * dV
+            const unsigned u0 = (unsigned)((h0 & 0x7fffffff) | fx0) - 0x20000000u, u1 = (unsigned)((h1 & 0x7fffffff) | fx1) - 0x20000000u;
+            if (max(u0, u1) >= 0x5ff00000u) {
+                const double sc = IWB_SUM_RHO ? P.dV : 1.0;
+                if (om0 && u0 >= 0x5ff00000u) {
+                    const double ev = em0 * sc;
+                    if (ev == 0.0) cnt3 += 0x10000 - (int)((unsigned)hm0 >> 31);
+                    else if (ev != ev) cnt3 += 0x100 - (int)((unsigned)hm0 >> 31);
+                }
+                if (om1 && u1 >= 0x5ff00000u) {
+                    const double ev = em1 * sc;
+                    if (ev == 0.0) cnt3 += 0x10000 - (int)((unsigned)hm1 >> 31);
+                    else if (ev != ev) cnt3 += 0x100 - (int)((unsigned)hm1 >> 31);
+                }
+            }
+            if (NSH > 0) {
+                constexpr int RB = RJ * 8;
+                if (xxi > lds_f64<RB>(ya)) return;          // no column of this row inside any shell (warp-uniform)
+                bool row_in[NSHA];
+                bool mixed = false;
+#pragma unroll
+                for (int sh = 0; sh < NSH; ++sh) {
+                    row_in[sh] = (sh < NIN) && (xxi <= (sh == 0 ? lds_f64<2 * RB>(ya) : lds_f64<3 * RB>(ya)));
+                    mixed = mixed || !row_in[sh];
+                }
+                double s0 = 0.0, s1 = 0.0;                   // the evaluator's own s = (x*x + y*y) + z*z (float32 values in float32 mode)
+                if (mixed) {
+                    const double yyj = lds_f64<0>(ya);
+                    if (DT == IWB_F64) {
+                        const double sxy = xxi + yyj;
+                        s0 = sxy + zz0; s1 = sxy + zz1;
+                    } else {
+                        const float sxy = __fadd_rn((float)xxi, (float)yyj);
+                        s0 = (double)__fadd_rn(sxy, (float)zz0); s1 = (double)__fadd_rn(sxy, (float)zz1);
+                    }
+                }
+#pragma unroll
+                for (int sh = 0; sh < NSH; ++sh) {
+                    if (row_in[sh]) {
+                        sh_sum[sh] += t; sh_abs[sh] += ta; sh_cnt[sh] += npl;
+                    } else {
+                        // the reference's own mask multiply (float32 thresholds are float32 values: the compare is exact in double)
+                        const bool in0 = (s0 <= P.shell_thr[sh]), in1 = (s1 <= P.shell_thr[sh]);
+                        const double m0 = in0 ? 1.0 : 0.0, m1 = in1 ? 1.0 : 0.0;
+                        sh_sum[sh] = fma(em0, m0, sh_sum[sh]);
+                        sh_abs[sh] = fma(fabs(em0), m0, sh_abs[sh]);
+                        sh_sum[sh] = fma(em1, m1, sh_sum[sh]);
+                        sh_abs[sh] = fma(fabs(em1), m1, sh_abs[sh]);
+                        if (in0 && om0) ++sh_cnt[sh];
+                        if (in1 && om1) ++sh_cnt[sh];
+                    }
+                }
+            }
+        };
+#else
+        auto tally2 = [&](const double (&e)[2], unsigned ya, double xxi) {
+            const double yyj = lds_f64<0>(ya);
             const double em0 = __hiloint2double(__double2hiint(e[0]) & om0, __double2loint(e[0]) & om0);
             const double em1 = __hiloint2double(__double2hiint(e[1]) & om1, __double2loint(e[1]) & om1);
             acc_sum += em0; acc_abs += fabs(em0);
@@ -329,6 +516,8 @@ k_energy3d(const __grid_constant__ K3Params P)
             }
         };
 
+#endif
+
         // ---- one-sided value at a global face: ((a f0) + (b f1)) + (c f2) over three consecutive entries --------
         // `addr` is the entry AT the face, STEP the byte distance to its neighbour along the axis; `hi` selects the
         // far face (entries idx-2, idx-1, idx with a1 b1 c1) instead of the near one (idx, idx+1, idx+2 with a0 b0 c0).
@@ -366,8 +555,8 @@ k_energy3d(const __grid_constant__ K3Params P)
 #pragma unroll 1
 #endif
             for (int jr = ty; jr < RJ; jr += NW, A += ROWB, ya += NW * 8) {
-                const int jedge = (t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0);
-                if (doO && jr >= 2 && jr <= Tj + 1) {
+                const int jedge = (t_jlo && jr == o_lo) ? 1 : ((t_jhi && jr == o_hi) ? 2 : 0);
+                if (doO && jr >= o_lo && jr <= o_hi) {
                     const unsigned Ai = A + o_pxi, Ap = A + o_pxp, Am = A + o_pxm, Ay = A + o_py;
                     // column a = this lane, column b = lane + 32 (256 bytes further)
                     const double xpa = lds_f64<0>(Ap), xma = lds_f64<0>(Am);
@@ -382,7 +571,6 @@ k_energy3d(const __grid_constant__ K3Params P)
                     const double ykpb = lds_f64<256 + 8>(Ay), ykmb = lds_f64<256 - 8>(Ay);
                     const double zkpa = lds_f64<ZB + 8>(Ay), zkma = lds_f64<ZB - 8>(Ay);
                     const double zkpb = lds_f64<ZB + 256 + 8>(Ay), zkmb = lds_f64<ZB + 256 - 8>(Ay);
-                    const double yyj = lds_f64<0>(ya);
                     double pxx[2] = {cdivm<MODE>(xpa - xma, cx.h2, cx.rh2), cdivm<MODE>(xpb - xmb, cx.h2, cx.rh2)};
                     double pxy[2] = {cdivm<MODE>(xjpa - xjma, cy.h2, cy.rh2), cdivm<MODE>(xjpb - xjmb, cy.h2, cy.rh2)};
                     double pxz[2] = {cdivm<MODE>(xkpa - xkma, cz.h2, cz.rh2), cdivm<MODE>(xkpb - xkmb, cz.h2, cz.rh2)};
@@ -427,21 +615,21 @@ k_energy3d(const __grid_constant__ K3Params P)
                         rho2[a] = cdivm<MODE>(tr * tr - kk, P.c16pi, P.rc16pi);
                     }
                     if (EMIT) {
-                        const long long j = j0 - 2 + jr, k = k0 - hl + tx;
+                        const long long j = j0 - hj + jr, k = k0 - hl + tx;
                         double* dst = P.rho_out + ((long long)(i - P.i_begin) * P.n1 + j) * P.n2 + k;
                         if (cf0 & 16u) dst[0] = rho2[0];
                         if (cf1 & 16u) dst[32] = rho2[1];
                     }
 #if IWB_SUM_RHO
-                    tally2(rho2, yyj, xxi);        // sums of rho; the flush multiplies by dV (sign(e) == sign(rho): dV > 0)
+                    tally2(rho2, ya, xxi);        // sums of rho; the flush multiplies by dV (sign(e) == sign(rho): dV > 0)
 #else
                     const double e2[2] = {rho2[0] * P.dV, rho2[1] * P.dV};
-                    tally2(e2, yyj, xxi);
+                    tally2(e2, ya, xxi);
 #endif
                 }
                 if (doC && jr >= py_lo && jr <= py_hi) {
                     const unsigned Ah = A + o_ph, Aw = A + o_w;
-                    const bool z_row = (jr >= 2 && jr <= Tj + 1);
+                    const bool z_row = (jr >= o_lo && jr <= o_hi);
                     const double hjpa = lds_f64<R8>(Ah), hjma = lds_f64<-R8>(Ah);
                     const double hjpb = lds_f64<256 + R8>(Ah), hjmb = lds_f64<256 - R8>(Ah);
                     const double hkpa = lds_f64<8>(Ah), hkma = lds_f64<-8>(Ah);
@@ -486,7 +674,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                 const unsigned Am2 = A + o_m2;
                 const double yyA = lds_f64<0>(ya), yyB = lds_f64<NW * 8>(ya);
                 const double m2[4] = {lds_f64<0>(Am2), lds_f64<256>(Am2), lds_f64<ROWB>(Am2), lds_f64<ROWB + 256>(Am2)};
-                const bool origin = (p == P.i_zero) && (j0 - 2 + ty == P.j_zero || j0 - 2 + ty + NW == P.j_zero);
+                const bool origin = (p == P.i_zero) && (j0 - hj + ty == P.j_zero || j0 - hj + ty + NW == P.j_zero);
                 double f[4];
                 if (DT == IWB_F64) {
                     const double sA = xxp + yyA, sB = xxp + yyB;
@@ -523,14 +711,14 @@ k_energy3d(const __grid_constant__ K3Params P)
                     const double sxy = xxp + yyj;
                     const double s[2] = {sxy + zz0, sxy + zz1};
                     // the row through the origin (r == 0 at one lane) takes the reference flavour
-                    const bool origin_row = (p == P.i_zero) && (j0 - 2 + jr == P.j_zero);
+                    const bool origin_row = (p == P.i_zero) && (j0 - hj + jr == P.j_zero);
                     // (exotic grids / parameters fail the host's operand-range proof: reference flavour throughout)
                     if (MODE == 0) phi_exact_f64<2, true>(s, xp, pc, f, origin_row || !pc.prechecked);
                     else phi_fast_f64<2>(s, xp, pc, f, origin_row || !pc.prechecked);
                 } else {
                     const float sxy = __fadd_rn((float)xxp, (float)yyj);
                     const float s[2] = {__fadd_rn(sxy, (float)zz0), __fadd_rn(sxy, (float)zz1)};
-                    const bool origin_row = (p == P.i_zero) && (j0 - 2 + jr == P.j_zero);
+                    const bool origin_row = (p == P.i_zero) && (j0 - hj + jr == P.j_zero);
                     phi_exact_f32ref<2, true>(s, (float)xp, pc, f, origin_row || !pc.prechecked);
                 }
                 const unsigned Ap = A + o_p;
@@ -600,7 +788,17 @@ k_energy3d(const __grid_constant__ K3Params P)
             unsigned cw[NCW];
             {
                 int c[2 * NCW];
+#if IWB_TALLY == 2
+                // neg | NaN | zero were counted; every other output point of this thread in the interval is positive
+                int rows_out = 0;
+#pragma unroll
+                for (int jr = ty; jr < RJ; jr += NW) rows_out += (jr >= o_lo && jr <= o_hi) ? 1 : 0;
+                const int npts = npl * rows_out * (i_last - flush_from + 1);
+                c[0] = cnt3 & 0xff; c[2] = (cnt3 >> 16) & 0xff;
+                c[1] = npts - c[0] - c[2] - ((cnt3 >> 8) & 0xff);
+#else
                 c[0] = cnt3 & 0xff; c[1] = (cnt3 >> 8) & 0xff; c[2] = (cnt3 >> 16) & 0xff;     // neg, pos, zero
+#endif
 #pragma unroll
                 for (int s2 = 0; s2 < NSH; ++s2) c[3 + s2] = sh_cnt[s2];
                 if (NCNT & 1) c[NCNT] = 0;
@@ -663,14 +861,20 @@ k_energy3d(const __grid_constant__ K3Params P)
                         if (is_int) acc = __longlong_as_double(__double_as_longlong(acc) + __double_as_longlong(o));
                         else acc += o;
                     }
+#if IWB_TALLY != 2
                     // the zero field counted the masked (non-output) columns of every row as well
                     if (q == 4)
                         acc = __longlong_as_double(__double_as_longlong(acc) -
                                                    (long long)Tj * (RK - Tk) * (i_last - flush_from + 1));
+#endif
                 }
                 P.partial[((size_t)fb * ntiles + rnk) * ROW + slot] = acc;     // slot of the tile's schedule index
             }
+#if IWB_NBSYNC
+            __syncthreads();     // warps drift: without a CTA-wide step barrier the scratch needs its own guard before reuse
+#else
             // the scratch is rewritten at the next flush only, at least one step barrier from here
+#endif
             acc_sum = 0.0; acc_abs = 0.0; cnt3 = 0;
             flush_from = i_last + 1;
 #pragma unroll

@@ -22,7 +22,7 @@ struct ProfParams {
     const double *xx, *yy, *zz;   // squared coordinates as staged for k_energy3d
     const double* edges;          // [nb + 1]
     int n1, n2, i_begin, i_end, nb, dtype;
-    double inv_width;             // nb / edges[nb]: first guess of the bin, corrected against the edges
+    double inv_width;             // nb / (edges[nb] - edges[0]): first guess of the bin, corrected against the edges
     double* part_sum;             // [flush block][PROF_SUB][nb]
     long long* part_cnt;
 };
@@ -56,10 +56,13 @@ static __global__ void __launch_bounds__(PROF_NW * 32) k_radial_hist(const ProfP
                 // the same r as the evaluator's (reproduce_rodal_exact.py:179, 218)
                 r = (P.dtype == IWB_F64) ? sqrt(sxy + P.zz[k]) : (double)__fsqrt_rn(__fadd_rn(sxy_f, (float)P.zz[k]));
             }
-            int kb = min((int)(r * P.inv_width), nb - 1);
+            // first guess from the mean bin width, then corrected against the edges themselves; the masks of
+            // tail.py:75 are (R >= e[k]) & (R < e[k+1]), so a point below the first edge or on / beyond the last
+            // one belongs to no bin
+            int kb = max(0, min((int)((r - s_edges[0]) * P.inv_width), nb - 1));
             while (kb > 0 && r < s_edges[kb]) --kb;
             while (kb < nb && r >= s_edges[kb + 1]) ++kb;     // kb == nb: on or beyond the last edge, in no bin
-            const bool in_bin = valid && kb < nb;
+            const bool in_bin = valid && kb < nb && r >= s_edges[0];
             unsigned todo = __ballot_sync(0xffffffffu, in_bin);
             while (todo) {
                 const int b = __shfl_sync(0xffffffffu, kb, __ffs(todo) - 1);

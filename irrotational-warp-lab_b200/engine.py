@@ -237,6 +237,12 @@ class Engine:
                                                    C.byref(bd), C.byref(bs), C.byref(sk)))
         return {"div_mismatches": bd.value, "sqrt_mismatches": bs.value, "skipped": sk.value}
 
+    def selftest_phi(self, *, rho=5.0, sigma=4.0, v=1.0, eps=1e-12, coord_lo=0.05, coord_hi=66.0, count=1 << 26, seed=1):
+        bad, wall = C.c_uint64(), C.c_uint64()
+        _capi.check(self._lib.iwb_selftest_phi(self._h, float(rho), float(sigma), float(v), float(eps), float(coord_lo),
+                                               float(coord_hi), int(count), int(seed), C.byref(bad), C.byref(wall)))
+        return {"mismatches": bad.value, "wall_points": wall.value}
+
     def selftest_constdiv(self, divisor, count=1 << 26, seed=1):
         bad = C.c_uint64()
         _capi.check(self._lib.iwb_selftest_constdiv(self._h, float(divisor), int(count), int(seed), C.byref(bad)))

@@ -46,8 +46,14 @@ def _sweep_record(v, e_pos_r1, e_neg_r1, e_pos_r2, e_neg_r2, r1, r2, elapsed):
 
 def sweep_velocity(*, mode: str, rho: float, sigma: float, v_values: list, extent: float,
                    tail_r1_mult: float, tail_r2_mult: float, backend: str = BACKEND_NAME, dtype: str = "float64",
-                   nx: int = None, ny: int = None, n: int = None, group=None) -> dict:
-    """Velocity sweep; same result dictionary as the reference (sweep_superluminal.py:97-121)."""
+                   nx: int = None, ny: int = None, n: int = None, group=None, distributed: bool = False) -> dict:
+    """Velocity sweep; same result dictionary as the reference (sweep_superluminal.py:97-121).
+
+    By default every calling process evaluates every point, like the reference.  With ``distributed=True`` (or an
+    explicit ``group``) the call is COLLECTIVE: every rank of the group must make it with the same arguments; the
+    points are dealt round-robin to the ranks and the records are all-gathered, so every rank returns the full
+    result.  A process that merely has ``torch.distributed`` initialised is never partitioned without asking.
+    """
     if backend != BACKEND_NAME:
         raise ValueError(f"Unknown backend: {backend!r} (expected: b200)")
     v_values = [float(v) for v in v_values]
@@ -55,7 +61,9 @@ def sweep_velocity(*, mode: str, rho: float, sigma: float, v_values: list, exten
         raise ValueError("v_values is empty")      # the reference dies with UnboundLocalError here
     r1, r2 = tail_r1_mult * rho, tail_r2_mult * rho
     rank, world = 0, 1
-    if group is not None or _dist_ready():
+    if group is not None or distributed:
+        if not _dist_ready():
+            raise RuntimeError("sweep_velocity(distributed=True) needs an initialised torch.distributed process group")
         import torch.distributed as dist
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     mine = partition_points(len(v_values), rank, world)

@@ -40,7 +40,7 @@ def _worker(rank, world, port, out_dir):
                 out[f"{n}_{dtype}_{shard}"] = [run["energies"]["e_pos"].hex(), run["energies"]["e_neg"].hex(), run["counts"]["neg"],
                                                run["_e_at_r"](40.0)[0].hex(), extra[0].hex(), extra[1].hex()]
         sw = sweeps.sweep_velocity(mode="3d", rho=5.0, sigma=4.0, v_values=[1.0, 1.5, 2.0, 2.5, 3.0], extent=66.0,
-                                   tail_r1_mult=8.0, tail_r2_mult=12.0, n=64)
+                                   tail_r1_mult=8.0, tail_r2_mult=12.0, n=64, distributed=True)   # collective: points dealt to ranks
         out["sweep"] = [r["e_pos_inf"].hex() for r in sw["sweep_results"]]
         json.dump(out, open(os.path.join(out_dir, f"rank{rank}.json"), "w"))
     finally:

@@ -158,3 +158,28 @@ def test_einstein_oracle(name):
     assert np.array_equal(np.ascontiguousarray(srt.real).reshape(-1)[idx], val)
     idx, val = _samples(rec, "eig_sorted_im_samples")
     assert np.array_equal(np.ascontiguousarray(srt.imag).reshape(-1)[idx], val)
+
+
+@pytest.mark.parametrize("name", ["n400", "n512"])
+def test_c_oracle_against_large_reference_golden(name):
+    """The chunked C oracle against the reference's own n = 400 / n = 512 results (tests/golden/make_golden_large.py):
+    this is what licenses its n = 1024 full-volume answer as the checker of the headline configuration."""
+    from conftest import load_golden, rel
+    from oracle import oracle_c
+    rec = load_golden("golden_3d_large.json")[name]
+    kw = rec["params"]
+    o = oracle_c.energy_3d_chunked(chunk=64, shells=[s["r"] for s in rec["shells"]], **kw)
+    assert (o["cnt_pos"], o["cnt_neg"], o["cnt_zero"]) == (rec["cnt_pos"], rec["cnt_neg"], rec["cnt_zero"])
+    assert rel(o["e_pos"], rec["energies"]["e_pos"]) < 1e-12 and rel(o["e_neg"], rec["energies"]["e_neg"]) < 1e-12
+    for so, sr in zip(o["shells"], rec["shells"]):
+        assert so["cnt"] == sr["cnt"]
+        assert rel(so["e_pos"], sr["e_pos"]) < 1e-12 and rel(so["e_neg"], sr["e_neg"]) < 1e-12
+
+
+def test_large_golden_matches_the_published_convergence_series():
+    """SURVEY App. B lists the reference's n = 400 and n = 512 energies; the frozen file must carry the same numbers."""
+    from conftest import load_golden
+    g = load_golden("golden_3d_large.json")
+    assert g["n400"]["energies"]["e_pos"] == 1.0501420768391059 and g["n400"]["energies"]["e_neg"] == -0.9978001009248166
+    assert g["n512"]["energies"]["e_pos"] == 1.0581107957495273 and g["n512"]["energies"]["e_neg"] == -1.0057397631812819
+    assert g["n1024"]["source"] == "oracle_c" and g["n400"]["source"] == "reference"
