@@ -3,26 +3,27 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--n 1024] [--impl ours|reference]
 
-One *step* = one full evaluation of the hot path on the synthetic (analytic) grid rho=5 sigma=4
-v=1 extent=66, shells r<=40 / r<=60: fused kernel -> fixed-order tile reduction -> (N>1: NCCL
-all-gather of the 245 KB chain sums) -> fixed-order row reduction -> 240-byte result to the host.
-
-N = 1 runs in this process; N > 1 is launched by torchrun, one rank per GPU, each rank owning an
-interleaved shard of the (j, k) tiles along the whole of axis 0 (weak scaling is NOT used: the volume
-is fixed, so "scaling": "strong").
+One *step* = one full evaluation of the hot path on the synthetic (analytic) grid rho=5 sigma=4 v=1 extent=66, shells
+r<=40 / r<=60.  One GPU: fused kernel -> fixed-order tile reduction -> fixed-order row reduction.  N > 1 (torchrun, one
+rank per GPU): every rank marches an interleaved shard of the (j, k) tiles along the whole of axis 0, pushes its chain
+sums into every rank's gathered buffer as NVLink peer stores, and combines them with the single-GPU tree (bit-identical
+energies on every rank; the NCCL all-gather is the fall-back when the ranks cannot map each other's memory).  The
+volume is fixed, so "scaling": "strong".
 
 Printed JSON (one line, rank 0):
-  value   : Gpoints/s, whole job, inputs (coordinates) resident in HBM -- CUDA events on the
-            launching stream, summed over K steps, max over ranks; on one GPU the result row of every
-            step stays on the device and all K are read (and checked against the warm-up's) after the
-            closing barrier, on several GPUs every step ends with the blocking read of its result
-  e2e     : same metric through the public API (backend.compute_energy_3d / distributed.
-            compute_energy_3d_sharded) with host numpy coordinates copied from pinned memory and the
-            result read back every step, wall clock
-  roofline: FP64-pipe bound (no dense contraction, ~0 HBM bytes/point); see DESIGN.md §6
+  value   : Gpoints/s, whole job, coordinates resident in HBM -- per-step CUDA-event pairs on the launching stream,
+            summed over K steps, max over ranks.  For every N the result row of each timed step stays on the device;
+            all K rows are read after the closing barrier and must equal the warm-up's result.
+  e2e     : same metric through the public API (backend.compute_energy_3d / distributed.compute_energy_3d_sharded):
+            host numpy coordinates staged through pinned memory and the 240-byte result read back EVERY step, wall clock
+  parity  : the run's result against the frozen full-volume answer (tests/golden/golden_3d_large.json): energies
+            <= 1e-10 relative, sign counts and shell point counts exact -- asserted, not just reported
+  multi_gpu_parity (N > 1): slab-mode, NCCL-exchange, unseen-radius and rank-dealt sweep results against rank 0's
+            single-GPU answers, bit for bit
+  roofline: FP64-pipe bound (no dense contraction, ~0 HBM bytes/point); see DESIGN.md section 6
   cpu_baseline: the NumPy restatement of the reference (oracle/oracle_np.py) on every host core, bounded sample
-`--impl reference` times that CPU path alone, on every host core (worker processes over slabs of the sample volume;
-the reference itself is pure NumPy, single-threaded).
+`--impl reference` times that CPU path alone with the same --steps / --warmup, on every host core (worker processes over
+slabs of the sample volume; the reference itself is single-threaded NumPy and needs ~240 GB at n = 1024^3).
 """
 from __future__ import annotations
 
@@ -44,19 +45,39 @@ import numpy as np  # noqa: E402
 RHO, SIGMA, V, EXTENT = 5.0, 4.0, 1.0, 66.0
 SHELLS = [40.0, 60.0]
 METRIC = "3D Gpoints/s (fp64, n=1024^3)"
-# FP64 issue slots per grid point.  CONTRACT = SURVEY.md §8(d) / BASELINE.md §4 (IEEE divisions at 9 slots
-# each, exp/log1p on every point).  EXACT_ALG = the bit-exact algorithm this engine runs, each grid point
-# evaluated once (no halo recompute), from the ncu per-instruction counts of the hot loops divided by their
-# geometric redundancy: phi 35 (sqrt 8, two divisions 2 x 6, other 15), nine
-# derivatives x 4, rho*dV 19, sums 5.  The kernel EXECUTES 113 FP64 instructions per point (halo recompute).
+# FP64 issue slots per grid point.  CONTRACT = SURVEY.md 8(d) / BASELINE.md 4 (IEEE divisions at 9 slots each, exp/log1p
+# on every point).  EXACT_ALG = the bit-exact algorithm this engine runs with every grid point evaluated once (no halo
+# recompute): phi 32 (sqrt 8, division with a seeded reciprocal 4, the other 5, remaining arithmetic 15), nine
+# derivatives x 4 = 36, rho * dV 19, sums 5 (round 1 counted 95 with two 6-slot divisions).
 SLOTS_CONTRACT = 271.0
-SLOTS_EXACT_ALG = 95.0
-CPU_SAMPLE_N = 256
-# dram__bytes_read.sum + dram__bytes_write.sum of k_energy3d, one launch at n = 1024^3 on one GPU, from the
-# committed `ncu --set full` capture of the same kernel launch (profiles/r1_k_energy3d_n1024_session2_summary.txt)
-# (111 616 B read, 0 B written in the capture of the final kernel; 490 496 B in the one before -- coordinate and
-# instruction fetches, it varies with the state of the L2)
+SLOTS_EXACT_ALG = 92.0
+# per-launch figures of k_energy3d at n = 1024^3 on one GPU from the committed `ncu --set full` capture of this build
+# (profiles/r2_k_energy3d_n1024_summary.txt): executed FP64 thread instructions per point, DRAM bytes read + written
+NCU_CAPTURE = "profiles/r2_k_energy3d_n1024_summary.txt"
+NCU_FP64_EXECUTED_PER_POINT = 103.6
 NCU_DRAM_BYTES_PER_LAUNCH = 111616 + 0
+CPU_SAMPLE_N = 256
+FP64_LANES_PER_SM = 64
+
+
+def workload_config(n):
+    """The `config` block: identical in both arms (the driver compares them)."""
+    return {
+        "workload": f"3D n={n}^3 fp64 energy-condition evaluation (BASELINE config 4): rho=5 sigma=4 v=1 extent=66, "
+                    f"shells r<=40 and r<=60, exact (IEEE-replay) mode",
+        "n": n, "rho": RHO, "sigma": SIGMA, "v": V, "extent": EXTENT, "shells": SHELLS, "dtype": "float64", "mode": "exact",
+        "l2": "GPU arm: a 256 MiB buffer is written between timed steps (the inputs are 32 KB of coordinates); "
+              "CPU arm: not applicable",
+        "timing": "GPU arm: per-step CUDA-event pairs on the launching stream, summed, max over ranks; CPU arm: wall clock",
+    }
+
+
+def load_golden_case(name):
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "golden_3d_large.json")) as f:
+            return json.load(f)["cases"].get(name)
+    except OSError:
+        return None
 
 
 class ClockSampler:
@@ -109,18 +130,21 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the NumPy restatement of the reference on every host core
+# ---------------------------------------------------------------------------------------------------------------------
 def _reference_slab(bounds):
-    """Worker of the reference arm: the NumPy port on planes [a, b) of the sample volume (2-plane overlap recomputed)."""
+    """Worker: the NumPy port on planes [a, b) of the sample volume (its 2-plane phi halo recomputed)."""
     from oracle import oracle_np
     a, b = bounds
     r = oracle_np.energy_3d(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, n=CPU_SAMPLE_N, shells=SHELLS, i_begin=a, i_end=b)
     return r["e_pos"], r["e_neg"]
 
 
-def _reference_timed(steps, warmup=1):
-    """The NumPy port of the reference path on every host core: the sample volume (n = CPU_SAMPLE_N) is cut into slabs of
-    axis 0 that worker processes evaluate independently, as the reference's own convergence_study_3d.py fans out over
-    subprocesses (the reference itself is single-threaded NumPy).  Returns seconds per step and the worker count."""
+def _reference_timed(steps, warmup):
+    """`warmup` untimed + `steps` timed evaluations of the sample volume (n = CPU_SAMPLE_N), cut into slabs of axis 0 that
+    worker processes evaluate independently -- the reference's own convergence_study_3d.py fans out over subprocesses
+    in the same way; the reference itself is single-threaded NumPy.  Returns seconds per step and the worker count."""
     import multiprocessing as mp
     n = CPU_SAMPLE_N
     try:
@@ -138,62 +162,182 @@ def _reference_timed(steps, warmup=1):
         for _ in range(steps):
             parts = pool.map(_reference_slab, slabs)
         dt = (time.perf_counter() - t0) / steps
-    e_pos = sum(p[0] for p in parts)
-    assert 1.02 < e_pos < 1.04, e_pos          # n = 256: 1.0274931410661474
+    e_pos, e_neg = sum(p[0] for p in parts), sum(p[1] for p in parts)
+    # n = 256: the reference gives 1.0274931410661474 / -0.9752262663519845 (tests/golden/golden_3d.json)
+    assert abs(e_pos - 1.0274931410661474) < 1e-12 and abs(e_neg + 0.9752262663519845) < 1e-12, (e_pos, e_neg)
     return dt, cores, avail, len(slabs)
 
 
 def _reference_record(dt, cores, avail, nslabs, n_full):
     n = CPU_SAMPLE_N
     return {"value": n ** 3 / dt / 1e9, "unit": "Gpoints/s", "cores": cores, "kind": "port",
-            "sample": f"each step = one n={n}^3 evaluation (bounded sample of the n={n_full}^3 workload: the reference needs "
-                      f"~224 B/point, i.e. ~240 GB at 1024^3) as {nslabs} slabs of axis 0 on {cores} worker processes; "
-                      f"NumPy port oracle/oracle_np.py (the reference itself is single-threaded)",
+            "sample_n": n,
+            "sample": f"each step = one n={n}^3 evaluation, a bounded sample of the n={n_full}^3 workload (the reference needs "
+                      f"~224 B/point, i.e. ~240 GB at 1024^3; its points/s does not depend on n), as {nslabs} slabs of axis 0 "
+                      f"on {cores} worker processes; NumPy port oracle/oracle_np.py, bit-equal to the reference on the golden "
+                      f"grids (the reference itself is single-threaded; /root/reference does not exist on the GPU box)",
             "host_cores_available": avail}
 
 
-def cpu_baseline(n_full=1024, reps=2):
-    """cpu_baseline leg of the main arm: the same measurement as `--impl reference`, two steps."""
-    return _reference_record(*_reference_timed(reps), n_full)
+def cpu_baseline(n_full=1024, reps=3):
+    """cpu_baseline leg of the main arm: the same measurement as `--impl reference`, a few steps."""
+    return _reference_record(*_reference_timed(reps, 1), n_full)
 
 
 def run_reference(args):
-    """--impl reference: the reference's own algorithm on the host, every core (see _reference_timed)."""
+    """--impl reference: the reference's own algorithm on the host, every core, --steps / --warmup honoured."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = min(max(args.steps, 1), 5)
-    dt, cores, avail, nslabs = _reference_timed(steps)
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    dt, cores, avail, nslabs = _reference_timed(steps, warmup)
     rec = _reference_record(dt, cores, avail, nslabs, args.n)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": rec["value"], "unit": "Gpoints/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3D n={args.n}^3 fp64 energy-condition evaluation (BASELINE config 4): rho=5 sigma=4 v=1 "
-                               f"extent=66, shells r<=40 and r<=60, exact (IEEE-replay) mode"},
+        "config": workload_config(args.n),
         "cpu_baseline": rec,
         "e2e": {"value": rec["value"], "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def check_parity(res, n):
+    """The run's result against the frozen answer for this grid (None when no golden exists for n)."""
+    rec = load_golden_case(f"n{n}")
+    if rec is None:
+        return None
+    rel = lambda a, b: abs(a - b) / max(abs(b), 1e-300)      # noqa: E731
+    out = {
+        "against": f"tests/golden/golden_3d_large.json:n{n} ({rec['source']}"
+                   + ("; the reference cannot run this size, the generating script validated the C oracle against the "
+                      "reference's n=400 and n=512 runs)" if rec["source"] != "reference" else ")"),
+        "e_pos_rel_err": rel(res["e_pos"], rec["energies"]["e_pos"]),
+        "e_neg_rel_err": rel(res["e_neg"], rec["energies"]["e_neg"]),
+        "counts_exact": (res["cnt_pos"], res["cnt_neg"], res["cnt_zero"]) == (rec["cnt_pos"], rec["cnt_neg"], rec["cnt_zero"]),
+        "shell_counts_exact": list(res["shell_cnt"]) == [s["cnt"] for s in rec["shells"]],
+        "shell_rel_err": max(max(rel(res["shell_pos"][k], s["e_pos"]), rel(res["shell_neg"][k], s["e_neg"]))
+                             for k, s in enumerate(rec["shells"])),
+        "tolerance": 1e-10,
+    }
+    out["ok"] = bool(out["e_pos_rel_err"] <= 1e-10 and out["e_neg_rel_err"] <= 1e-10 and out["shell_rel_err"] <= 1e-10
+                     and out["counts_exact"] and out["shell_counts_exact"])
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config 5: 20-point superluminal sweep + 50-point optimiser batch, 3D n = 256, spread over the GPUs
+# ---------------------------------------------------------------------------------------------------------------------
+def run_sweep_opt(args):
+    """`--config sweep_opt`: one step = the 20 sweep evaluations of sweeps.sweep_velocity (v = 1..3) plus the 50 objective
+    evaluations of optimize.evaluate_objective_3d_batch ((sigma, v) drawn with seed 42 from [2, 8] x [0.8, 2.0], the box and
+    budget of the reference README's Bayesian run), all 3D n = 256^3, rho = 5.  N > 1: both calls deal their points
+    round-robin to the ranks.  Timed through the public API with host buffers: wall clock between barriers, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from irrotational_warp_lab_b200 import optimize, sweeps
+    from irrotational_warp_lab_b200.engine import get_engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    get_engine(local_rank)
+    n = 256
+    v_values = np.linspace(1.0, 3.0, 20).tolist()
+    gold = load_golden_case("objective_n256")
+    rng = np.random.default_rng(42)
+    pts = [(p["sigma"], p["v"]) for p in gold["points"]] if gold else []
+    pts += [(float(s), float(v)) for s, v in zip(rng.uniform(2.0, 8.0, 50 - len(pts)), rng.uniform(0.8, 2.0, 50 - len(pts)))]
+    dkw = dict(distributed=True) if world > 1 else {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        sw = sweeps.sweep_velocity(mode="3d", rho=RHO, sigma=SIGMA, v_values=v_values, extent=EXTENT, tail_r1_mult=8.0,
+                                   tail_r2_mult=12.0, n=n, **dkw)
+        vals = optimize.evaluate_objective_3d_batch(pts, RHO, EXTENT, n, **dkw)
+        return sw, vals
+
+    warmup, steps = max(args.warmup, 3), max(args.steps, 1)
+    for _ in range(warmup):
+        sw, vals = step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sw, vals = step()
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    nev = len(v_values) + len(pts)
+    # parity: the frozen reference objective values, and E proportional to v^2 along the sweep (SURVEY App. B: to 1e-15)
+    rel = lambda a, b: abs(a - b) / max(abs(b), 1e-300)      # noqa: E731
+    obj_err = max((rel(vals[k], p["abs_e_neg"]) for k, p in enumerate(gold["points"])), default=None) if gold else None
+    e1 = sw["sweep_results"][0]["e_pos_inf"]
+    v2_err = max(rel(r["e_pos_inf"], e1 * r["v"] ** 2) for r in sw["sweep_results"])
+    assert (obj_err is None or obj_err < 1e-10) and v2_err < 1e-12, (obj_err, v2_err)
+    if rank == 0:
+        from oracle import oracle_np
+        t1 = time.perf_counter()
+        oracle_np.energy_3d(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, n=n, shells=SHELLS)
+        t_cpu = time.perf_counter() - t1
+        print(json.dumps({
+            "metric": "config-5 evaluations/s (20-point v sweep + 50-point optimiser batch, 3D n=256^3)",
+            "value": nev * steps / dt, "unit": "evaluations/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE config 5: sweeps.sweep_velocity (v = 1..3, 20 points) + "
+                                   "optimize.evaluate_objective_3d_batch (50 (sigma, v) points, seed 42, sigma in [2, 8], v in "
+                                   "[0.8, 2.0]), 3D n=256^3, rho=5, exact mode; points dealt round-robin to the ranks",
+                       "evaluations_per_step": nev, "n": n},
+            "gpoints_per_s": nev * steps * n ** 3 / dt / 1e9,
+            "timing": "public API, host buffers in / Python floats out every evaluation; wall clock between barriers, max over ranks",
+            "parity": {"objective_rel_err_vs_reference_golden": obj_err, "sweep_v2_scaling_rel_err": v2_err},
+            "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "evaluations/s", "cores": 1, "kind": "port",
+                             "sample": "one n=256^3 evaluation of the NumPy port (the reference evaluates the points serially, "
+                                       "single-threaded)"},
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", choices=["headline", "sweep_opt"], default="headline",
+                    help="headline: BASELINE config 4 (the driver's line); sweep_opt: BASELINE config 5")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--n", type=int, default=1024)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--exchange", choices=["auto", "peer", "nccl"], default="auto",
+                    help="N > 1: how the chain sums travel (NVLink peer stores fused behind the kernel, or NCCL all-gather)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args(argv)
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "sweep_opt":
+        return run_sweep_opt(args)
 
     import torch
     import torch.distributed as dist
 
-    from irrotational_warp_lab_b200 import backend, distributed, sharding
-    from irrotational_warp_lab_b200 import _capi
+    from irrotational_warp_lab_b200 import _capi, backend, distributed, sharding, sweeps
     from irrotational_warp_lab_b200._capi import ROW_WIDTH, TILE_CHAINS
     from irrotational_warp_lab_b200.engine import get_engine
 
@@ -220,6 +364,11 @@ def main(argv=None):
     i_begin, i_end = (0, n) if (world == 1 or tiles is not None) else sharding.slab_bounds(n, world)[rank]
     nfb = sharding.num_flush_blocks(n)
     r0, r1 = sharding.rows_of_slab(i_begin, i_end)
+    peers = None
+    if tiles is not None and args.exchange != "nccl":
+        peers = distributed.peer_group_for(eng, None, nfb)
+        if peers is None and args.exchange == "peer":
+            raise SystemExit("--exchange peer: the ranks cannot map each other's device memory")
 
     def barrier():
         if world > 1:
@@ -236,67 +385,56 @@ def main(argv=None):
         table = torch.zeros((nfb, ROW_WIDTH), dtype=torch.float64, device=dev)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
-
-    def resident_step():
-        if plan is not None:
-            plan.run_async(table.data_ptr(), stream.cuda_stream)
-        if tiles is not None:
-            full = sharding.all_gather_chains(table, world)
-            return eng.reduce_chains(full.data_ptr(), world, nfb, len(SHELLS), stream.cuda_stream)
-        full = sharding.all_gather_table(table[r0:r1], n, world) if world > 1 else table
-        return eng.reduce_table(full.data_ptr(), nfb, len(SHELLS), stream.cuda_stream)
-
     # nvidia-smi is started BEFORE the warm-up and given time to initialise NVML: its start-up briefly stalls the driver,
     # which showed up as 0.2-0.3 ms outliers in the 1.4 ms steps of an 8-GPU run when it fell into the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.5)
-    # Timed steps: the same launches with nothing read back in between -- the result row of every step stays on the
-    # device (k_reduce_rows writes it to rows_out[s]) and all K rows are read after the closing synchronisation, so no host
-    # thread sits inside the per-step event pairs (a late one used to show up as a 1-2 ms outlier in one step of ten).
-    rows_out = torch.zeros((steps, ROW_WIDTH), dtype=torch.float64, device=dev)
+    # Every step leaves its result row on the device (rows_out[s]); nothing is read back inside the timed region, so no
+    # host thread sits inside the per-step event pairs -- the same flavour for every N.
+    rows_out = torch.zeros((warmup + steps, ROW_WIDTH), dtype=torch.float64, device=dev)
     scratch_tab = torch.empty((nfb, ROW_WIDTH), dtype=torch.float64, device=dev)
     keep_alive = []
 
-    def resident_step_async(s):
+    def resident_step(s):
+        row = rows_out[s].data_ptr()
+        if peers is not None:
+            plan.run_exchange_async(peers, row, stream.cuda_stream)          # k_energy3d, push over NVLink, combine
+            return
         if plan is not None:
             plan.run_async(table.data_ptr(), stream.cuda_stream)
         if tiles is not None:
             full = sharding.all_gather_chains(table, world)
             keep_alive.append(full)
-            eng.reduce_chains_async(full.data_ptr(), world, nfb, scratch_tab.data_ptr(), rows_out[s].data_ptr(), stream.cuda_stream)
+            eng.reduce_chains_async(full.data_ptr(), world, nfb, scratch_tab.data_ptr(), row, stream.cuda_stream)
         else:
             full = sharding.all_gather_table(table[r0:r1], n, world) if world > 1 else table
             keep_alive.append(full)
-            eng.reduce_table_async(full.data_ptr(), nfb, rows_out[s].data_ptr(), stream.cuda_stream)
+            eng.reduce_table_async(full.data_ptr(), nfb, row, stream.cuda_stream)
 
-    for _ in range(warmup):
-        res = resident_step()                   # blocking flavour: also the value the timed steps must reproduce
+    for s in range(warmup):
+        resident_step(s)
+    torch.cuda.synchronize(dev)
+    res = eng.read_row(rows_out[warmup - 1].data_ptr(), len(SHELLS), stream.cuda_stream)     # what the timed steps must reproduce
+    res["cnt_nan"] = n ** 3 - res["cnt_pos"] - res["cnt_neg"] - res["cnt_zero"]
     gc.collect()
     gc.disable()          # no collector pauses between the launches of the timed steps (one late rank delays every rank)
     barrier()
     t_region0 = time.perf_counter()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    # (the non-blocking flavour is used on one GPU, where it was validated on hardware; multi-GPU steps keep the blocking
-    # read of the result, their outliers came from the clock sampler's start-up and are gone)
-    use_async = (world == 1)
     for s in range(steps):
         flush_buf.zero_()                       # L2 flush between timed iterations (outside the event pair)
         ev[s][0].record(stream)
-        if use_async:
-            resident_step_async(s)
-        else:
-            res = resident_step()
+        resident_step(warmup + s)
         ev[s][1].record(stream)
     barrier()
     t_region1 = time.perf_counter()
-    if use_async:
-        rows_host = rows_out.cpu().numpy()
-        for s in range(steps):
-            got = sharding.reduce_table_host(rows_host[s:s + 1], len(SHELLS))
-            assert (got["e_pos"], got["e_neg"], got["cnt_neg"], got["cnt_pos"]) == \
-                   (res["e_pos"], res["e_neg"], res["cnt_neg"], res["cnt_pos"]), f"timed step {s} disagrees with the warm-up"
+    rows_host = rows_out.cpu().numpy()
+    for s in range(warmup + steps):
+        got = sharding.reduce_table_host(rows_host[s:s + 1], len(SHELLS))
+        assert (got["e_pos"], got["e_neg"], got["cnt_neg"], got["cnt_pos"]) == \
+               (res["e_pos"], res["e_neg"], res["cnt_neg"], res["cnt_pos"]), f"step {s} disagrees with the warm-up"
     keep_alive.clear()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     dev_ms = sum(step_ms)
@@ -308,10 +446,12 @@ def main(argv=None):
         dev_ms = float(t.item())
     ms_per_step = dev_ms / steps
     value = n ** 3 / (ms_per_step * 1e-3) / 1e9
-    # k_energy3d, k_reduce_tiles | k_chain_sums, (k_combine_chains,) k_reduce_rows
-    launches_value = steps * ((2 if plan is not None else 0) + (2 if tiles is not None else 1))
+    # own kernels per step: k_energy3d + (peer: k_chain_sums_push, k_exchange_combine | NCCL: k_chain_sums,
+    # k_combine_chains, k_reduce_rows | one GPU: k_reduce_tiles, k_reduce_rows)
+    per_step = (1 if plan is not None else 0) + (2 if (peers is not None or tiles is None) else 3)
+    launches_value = (warmup + steps) * per_step
 
-    # kernel-only duration of the dominant kernel (rank 0's slab), CUDA events on its launching stream
+    # kernel-only duration of the dominant kernel (this rank's share), CUDA events on its launching stream
     kern_ms = []
     if plan is not None:
         for _ in range(min(steps, 5)):
@@ -323,11 +463,13 @@ def main(argv=None):
             torch.cuda.synchronize(dev)
             kern_ms.append(a.elapsed_time(b))
     kern_ms_avg = sum(kern_ms) / max(len(kern_ms), 1)
+    launches_kernel_only = 2 * len(kern_ms)
 
     # ---------------- e2e: public API, host buffers, wall clock ------------------------------------------
     def api_step():
         if world > 1:
-            return distributed.compute_energy_3d_sharded(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, n=n, shells=SHELLS)
+            return distributed.compute_energy_3d_sharded(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, n=n, shells=SHELLS,
+                                                         exchange=args.exchange)
         return backend.compute_energy_3d(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, n=n, shells=SHELLS)
 
     for _ in range(warmup):
@@ -343,16 +485,50 @@ def main(argv=None):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = n ** 3 * steps / e2e_s / 1e9
-    launches_e2e = steps * (4 if tiles is not None else 3)
+    launches_e2e = (warmup + steps) * (3 if (world == 1 or peers is not None) else 4)
     gc.enable()
     if rank == 0:
         sampler.stop()
     clocks = sampler.summary(t_region0, time.perf_counter()) if rank == 0 else None
 
-    # sanity: the two paths agree bit-for-bit and look like the reference's convergence series
+    # the two paths agree bit for bit, and with the frozen full-volume answer
     assert run["energies"]["e_pos"] == res["e_pos"] and run["energies"]["e_neg"] == res["e_neg"], "paths disagree"
-    if n == 1024:
-        assert 1.058 < res["e_pos"] < 1.08 and -1.03 < res["e_neg"] < -1.005, res
+    assert run["counts"]["neg"] == res["cnt_neg"] and run["counts"]["pos"] == res["cnt_pos"], "paths disagree (counts)"
+    parity = check_parity(res, n)
+    if parity is not None:
+        assert parity["ok"], parity
+
+    # ---------------- N > 1: the other multi-process paths against rank 0's single-GPU answers --------------------
+    multi = None
+    if world > 1:
+        multi = {}
+        r_extra = 23.5
+        single = backend.compute_energy_3d(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, n=n, shells=SHELLS) if rank == 0 else None
+        single_extra = single["_e_at_r"](r_extra) if rank == 0 else None
+
+        def same_as_single(got, got_extra):
+            if rank != 0:
+                return True
+            return bool(got["energies"]["e_pos"] == single["energies"]["e_pos"] and got["energies"]["e_neg"] == single["energies"]["e_neg"]
+                        and got["counts"] == single["counts"] and tuple(got_extra) == tuple(single_extra))
+
+        for label, kw in (("tiles_" + ("peer" if peers is not None else "nccl"), dict(shard="tiles", exchange=args.exchange)),
+                          ("tiles_nccl", dict(shard="tiles", exchange="nccl")),
+                          ("slab_nccl", dict(shard="slab"))):
+            got = distributed.compute_energy_3d_sharded(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, n=n, shells=SHELLS, **kw)
+            extra = got["_e_at_r"](r_extra)            # a radius nobody asked for: collective relaunch
+            multi[label + "_equals_single_gpu"] = same_as_single(got, extra)
+        vs = [1.0, 1.5, 2.0, 2.5, 3.0]
+        sw = sweeps.sweep_velocity(mode="3d", rho=RHO, sigma=SIGMA, v_values=vs, extent=EXTENT, tail_r1_mult=8.0,
+                                   tail_r2_mult=12.0, n=128, distributed=True)          # points dealt round-robin to the ranks
+        if rank == 0:
+            sw1 = sweeps.sweep_velocity(mode="3d", rho=RHO, sigma=SIGMA, v_values=vs, extent=EXTENT, tail_r1_mult=8.0,
+                                        tail_r2_mult=12.0, n=128)
+            key = lambda d: [(r["v"], r["e_pos_inf"], r["e_neg_inf"], r["ratio_r2"]) for r in d["sweep_results"]]   # noqa: E731
+            multi["rank_dealt_sweep_equals_single_gpu"] = bool(key(sw) == key(sw1))
+            multi["unseen_radius"] = r_extra
+            assert all(v for k, v in multi.items() if k.endswith("_equals_single_gpu")), multi
+        barrier()
 
     if rank == 0:
         peak = eng.measure_fma_peak(False)
@@ -360,59 +536,71 @@ def main(argv=None):
         pts_per_s_kernel = kernel_points / (kern_ms_avg * 1e-3) if kern_ms_avg else 0.0
         achieved_contract = pts_per_s_kernel * SLOTS_CONTRACT * 2 / 1e12
         achieved_exact = pts_per_s_kernel * SLOTS_EXACT_ALG * 2 / 1e12
+        sm_max_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+        peak_nominal = eng.sm_count * FP64_LANES_PER_SM * 2 * sm_max_mhz * 1e6 / 1e12
         peaks_file = {}
         try:
             peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
         hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
-        # coordinates in; per-(flush block, tile) partial rows out (36 x 60 tiles of the default 40 x 64 geometry, 62 columns
-        # in the tiles at the k faces);
-        # they are consumed by k_reduce_tiles and usually never leave L2
+        # coordinates in; per-(flush block, tile) partial rows out, consumed by the tile reduction and usually never leaving L2
         ntiles = _capi.load().iwb_debug_tiles_j(n, None, 0) * _capi.load().iwb_debug_tiles_k(n, None, 0)
         alg_bytes = 8.0 * (2 * n + n + n) + 8.0 * ROW_WIDTH * (r1 - r0) * ntiles / (world if tiles is not None else 1)
+        cfg = workload_config(n)
         line = {
             "metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3D n={n}^3 fp64 energy-condition evaluation (BASELINE config 4): rho=5 sigma=4 v=1 "
-                                   f"extent=66, shells r<=40 and r<=60, exact (IEEE-replay) mode",
-                       "sharding": ("single GPU" if world == 1 else
-                                    f"{world} interleaved tile shards (every {world}-th 36x60 tile of the (j,k) plane, whole axis 0), "
-                                    f"all-gather of {nfb}x{TILE_CHAINS}x{ROW_WIDTH} f64 chain sums" if tiles is not None else
-                                    f"{world} slab(s) of axis 0, analytic halo recompute, all-gather of a {nfb}x{ROW_WIDTH} f64 table"),
-                       "l2": "256 MiB buffer written between timed steps (inputs are 32 KB of coordinates)",
-                       "timing": "per-step CUDA-event pairs on the launching stream, summed; max over ranks"},
+            "config": cfg,
+            "sharding": ("single GPU" if world == 1 else
+                         f"{world} interleaved tile shards (every {world}-th 36x60 tile of the (j,k) plane, whole axis 0); "
+                         + (f"{nfb}x{TILE_CHAINS}x{ROW_WIDTH} f64 chain sums pushed into every rank's buffer as NVLink peer stores "
+                            f"(k_chain_sums_push + k_exchange_combine, no NCCL launch)" if peers is not None else
+                            f"NCCL all-gather of {nfb}x{TILE_CHAINS}x{ROW_WIDTH} f64 chain sums") if tiles is not None else
+                         f"{world} slab(s) of axis 0, analytic halo recompute, all-gather of a {nfb}x{ROW_WIDTH} f64 table"),
             "e2e": {"value": e2e_value, "unit": "Gpoints/s", "h2d_bytes_per_step": 8 * 4 * n,
                     "d2h_bytes_per_step": 8 * ROW_WIDTH, "ms_per_step": e2e_s / steps * 1e3,
                     "api": "distributed.compute_energy_3d_sharded" if world > 1 else "backend.compute_energy_3d"},
-            "gpu_launches": launches_value + launches_e2e,
+            "gpu_launches": launches_value + launches_kernel_only + launches_e2e,
+            "parity": parity,
             "roofline": {
                 "bound": "fp64", "kernel": "k_energy3d", "unit": "TFLOP/s",
                 "achieved": achieved_exact, "peak": peak["tflops"], "frac": achieved_exact / peak["tflops"],
+                "peak_nominal": peak_nominal, "frac_nominal": achieved_exact / peak_nominal,
+                "peak_source": "register-resident DFMA microbenchmark run in this process (iwb_measure_fma_peak: one CTA of 16 "
+                               "warps per SM, 8 chains per thread; the pipe is 100 % busy, so this is lanes x the SM clock it ran "
+                               "at); MEASURED_PEAKS.json has no FP64 vector figure.  peak_nominal = SMs x 64 lanes x 2 x "
+                               "clocks.max.sm",
+                "peak_sm_mhz": peak["sm_mhz_effective"],
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (n == 1024 and world == 1) else None,
+                "traffic_source": NCU_CAPTURE if (n == 1024 and world == 1) else None,
                 "slots_per_point": SLOTS_EXACT_ALG,
-                "note": "FP64-pipe bound: achieved = kernel points/s x 95 FP64 issue slots/point x 2 (slots of the "
-                        "bit-exact algorithm with every point evaluated once, from ncu SASS counts, DESIGN.md §6; the "
-                        "kernel executes 113/point including the phi halo recompute); peak = register-resident DFMA "
-                        "microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 vector figure)",
+                "fp64_executed_per_point": NCU_FP64_EXECUTED_PER_POINT if n == 1024 else None,
+                "note": "FP64-pipe bound: achieved = kernel points/s x 92 FP64 issue slots/point x 2 -- the slots of the "
+                        "bit-exact algorithm with every point evaluated once (DESIGN.md section 6); the kernel executes more "
+                        "(fp64_executed_per_point, from the ncu capture named in traffic_source: phi is recomputed in the "
+                        "tile halos), which does not count as achieved work",
                 "kernel_ms": kern_ms_avg, "kernel_points": kernel_points,
                 "contract": {"slots_per_point": SLOTS_CONTRACT, "achieved": achieved_contract,
                              "frac": achieved_contract / peak["tflops"],
-                             "note": "SURVEY.md §8(d) figure (9-slot IEEE divisions, exp/log1p at every point)"},
+                             "note": "SURVEY.md 8(d) figure (9-slot IEEE divisions, exp/log1p at every point)"},
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kern_ms_avg * 1e-3) / 1e9
                         if kern_ms_avg else None, "peak_gbs": hbm_peak, "note": "never binding: ~0 B/point"},
-                "peak_sm_mhz_effective": peak["sm_mhz_effective"],
             },
             "clocks": clocks,
-            "result": {"e_pos": res["e_pos"], "e_neg": res["e_neg"], "cnt_neg": res["cnt_neg"], "cnt_pos": res["cnt_pos"]},
+            "result": {"e_pos": res["e_pos"], "e_neg": res["e_neg"], "cnt_neg": res["cnt_neg"], "cnt_pos": res["cnt_pos"],
+                       "cnt_zero": res["cnt_zero"], "shell_cnt": list(res["shell_cnt"])},
         }
+        if multi is not None:
+            line["multi_gpu_parity"] = multi
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(n)
         print(json.dumps(line))
     if plan is not None:
         plan.close()
     if world > 1:
+        barrier()
         dist.destroy_process_group()
     return 0
 

@@ -26,7 +26,9 @@
  *
  * Conventions: plain C, no torch / CUDA types.  All pointers are caller-owned
  * HOST memory unless a field says "device"; the library copies what it needs and
- * keeps nothing past return.  Every call is blocking and returns IWB_OK (0) or an
+ * keeps nothing past return.  Calls are blocking unless their name ends in _async
+ * (those enqueue work on the caller's stream and return; each uses its own staging
+ * slot, so calls on different streams do not interfere) and return IWB_OK (0) or an
  * error code; iwb_last_error() gives the thread-local message.  A handle is bound
  * to ONE device (one process per GPU is the multi-GPU model; the host layer does
  * the NCCL collective through torch.distributed) and is not thread-safe; use one
@@ -59,7 +61,10 @@ enum iwb_dtype {
     IWB_F64 = 0,       /* reference --dtype float64                                          */
     IWB_F32_REF = 1,   /* reference --dtype float32 as NumPy>=2 evaluates it: float32 grid,   */
                        /* r, log-cosh and cos(theta); float64 from sinh(rho*sigma) onwards    */
-    IWB_F32_STRICT = 2 /* everything in float32 (documented as outside the 1e-5 bar at large n) */
+    IWB_F32_STRICT = 2 /* float32 grid and EVERY operation of phi in float32 (FP32 pipe); the stencils run in   */
+                       /* float64 on the float32-valued field.  3D evaluator only.  No reference semantics: within */
+                       /* 1e-5 of the reference's float32 mode up to n ~ 200, outside it on finer grids (the phi    */
+                       /* rounding error is divided by dx^2) -- DESIGN.md section 2 has the measured error per n   */
 };
 
 enum iwb_mode {
@@ -142,6 +147,27 @@ int iwb_energy3d_tiles_async(iwb_handle *h, const iwb_params3d *p, double *chain
 int iwb_reduce_chains(iwb_handle *h, const double *gathered_device, int tile_stride, int nfb, int nshell, void *stream,
                       iwb_result *out);
 
+/* The tile-shard evaluation with the exchange fused in: instead of an NCCL all-gather, every rank's chain sums cross
+ * NVLink / NVSwitch as plain peer stores into the gathered buffer of every rank, followed by an epoch-flag handshake and
+ * the same chain tree + row sum as the single-GPU path (bit-identical energies on every rank, for every S).  Set-up, once
+ * per process group: every rank calls iwb_peer_create (allocates its buffers for grids of up to nfb_max flush blocks and
+ * returns an IWB_PEER_HANDLE_BYTES IPC handle), the HOST layer all-gathers the handles (rank-major), every rank calls
+ * iwb_peer_connect.  All ranks must reside on one node with peer access between their GPUs.
+ * iwb_energy3d_tiles_exchange_async is COLLECTIVE: every rank of the group calls it the same number of times with
+ * tile_stride = world, tile_first = rank; it enqueues k_energy3d, the push of the chain sums and the combine on `stream`
+ * and leaves the final row (IWB_ROW_WIDTH doubles) in `row_device` without synchronising.  iwb_read_row copies such a row
+ * to the host (blocking) and unpacks it. */
+#define IWB_PEER_HANDLE_BYTES 64
+typedef struct iwb_peer iwb_peer;
+int iwb_peer_create(iwb_handle *h, int rank, int world, int nfb_max, iwb_peer **out, void *handle_out);
+int iwb_peer_connect(iwb_peer *peer, const void *all_handles);
+int iwb_peer_destroy(iwb_peer *peer);
+int iwb_energy3d_tiles_exchange_async(iwb_handle *h, iwb_peer *peer, const iwb_params3d *p, void *stream, double *row_device);
+int iwb_read_row(iwb_handle *h, const double *row_device, int nshell, void *stream, iwb_result *out);
+/* Test hook: connects peers that live in ONE process on one device (IPC handles cannot be opened by the process that
+ * exported them) so that the single-GPU test-suite can run the exchange kernels with emulated ranks, one stream each. */
+int iwb_debug_peer_connect_local(iwb_peer *peer, iwb_peer *const *all_peers);
+
 /* Non-blocking halves of iwb_reduce_table / iwb_reduce_chains for callers that keep several evaluations in flight on one
  * stream: the final row (IWB_ROW_WIDTH doubles, layout of the table rows) is left in `row_device`; nothing is copied to
  * the host and nothing is synchronised.  `table_scratch_device` receives the [nfb][IWB_ROW_WIDTH] table of the chain tree. */
@@ -158,6 +184,9 @@ int iwb_plan3d_create(iwb_handle *h, const iwb_params3d *p, iwb_plan3d **out);
 /* table_device: the slab table of iwb_energy3d_slab_async, or -- for a plan with tile_stride > 1 -- the chain
  * buffer of iwb_energy3d_tiles_async. */
 int iwb_plan3d_run_async(iwb_plan3d *plan, double *table_device, void *stream);
+/* the prepared tile shard of a peer group (tile_stride = world, tile_first = rank) with the fused exchange: collective,
+ * no host<->device traffic, result row in `row_device` (see iwb_energy3d_tiles_exchange_async) */
+int iwb_plan3d_run_exchange_async(iwb_plan3d *plan, iwb_peer *peer, void *stream, double *row_device);
 int iwb_plan3d_destroy(iwb_plan3d *plan);
 
 /* Fixed-order sum of a complete table (device pointer) into *out; blocking. */

@@ -16,6 +16,7 @@ MAX_SHELLS = 8
 FLUSH_PLANES = 16
 TILE_CHAINS = 16
 ROW_WIDTH = 6 + 3 * MAX_SHELLS
+PEER_HANDLE_BYTES = 64
 
 OK, ERR_INVALID, ERR_GRID_TOO_SMALL, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM = range(6)
 F64, F32_REF, F32_STRICT = 0, 1, 2
@@ -113,11 +114,18 @@ SYMBOLS = {
     "iwb_energy3d": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.POINTER(Result)]),
     "iwb_energy3d_slab_async": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.c_void_p, C.c_void_p]),
     "iwb_energy3d_tiles_async": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.c_void_p, C.c_void_p]),
+    "iwb_peer_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]),
+    "iwb_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "iwb_peer_destroy": (C.c_int, [C.c_void_p]),
+    "iwb_debug_peer_connect_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "iwb_energy3d_tiles_exchange_async": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Params3D), C.c_void_p, C.c_void_p]),
+    "iwb_read_row": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Result)]),
     "iwb_reduce_chains": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(Result)]),
     "iwb_reduce_table_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "iwb_reduce_chains_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "iwb_plan3d_create": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.POINTER(C.c_void_p)]),
     "iwb_plan3d_run_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "iwb_plan3d_run_exchange_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "iwb_plan3d_destroy": (C.c_int, [C.c_void_p]),
     "iwb_reduce_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(Result)]),
     "iwb_radial_profile3d": (C.c_int, [C.c_void_p, C.POINTER(Params3D), C.POINTER(Profile3D), C.POINTER(Result)]),

@@ -6,6 +6,10 @@
                       (/root/reference/src/irrotational_warp/viz.py:30-105, flags of cli.py:16-25), with the optional
                       ``--einstein`` and ``--tail-correction`` blocks
 
+  * ``optimize``   <- ``python -m irrotational_warp optimize``           (/root/reference/src/irrotational_warp/cli.py:56-77, 179-276)
+                      plus ``--objective volume3d`` (BASELINE config 5)
+  * ``convergence``<- ``scripts/convergence_study_3d.py``              (/root/reference/scripts/convergence_study_3d.py:21-183)
+
     python -m irrotational_warp_lab_b200.cli reproduce --mode 3d --n 256 --out results/repro.json
     python -m irrotational_warp_lab_b200.cli sweep --mode 3d --n 80 --v-steps 20 --out results/sweep.json
 
@@ -199,15 +203,130 @@ def slice_main(argv=None) -> int:
     return 0
 
 
+def optimize_main(argv=None) -> int:
+    """``python -m irrotational_warp optimize`` (/root/reference/src/irrotational_warp/cli.py:56-77, 179-276): same flags
+    and result JSON; ``--objective volume3d`` swaps the 2D-slice objective for |E-| of the 3D exact-potential volume
+    (BASELINE config 5: ``--objective volume3d --n 256 --method bayes --n-calls 50``)."""
+    from . import optimize as opt
+    p = argparse.ArgumentParser(description="Find parameters minimizing negative energy magnitude |E-| on the B200 engine")
+    p.add_argument("--rho", type=float, default=10.0, help="Bubble radius (geometric units)")
+    p.add_argument("--sigma-min", type=float, default=1.0)
+    p.add_argument("--sigma-max", type=float, default=10.0)
+    p.add_argument("--sigma-steps", type=int, default=5, help="Grid search resolution (sigma)")
+    p.add_argument("--v-min", type=float, default=0.5)
+    p.add_argument("--v-max", type=float, default=2.0)
+    p.add_argument("--v-steps", type=int, default=5, help="Grid search resolution (v)")
+    p.add_argument("--extent", type=float, default=20.0, help="Half-width of the domain")
+    p.add_argument("--n", type=int, default=71, help="Grid resolution per axis")
+    p.add_argument("--method", type=str, default="hybrid", choices=["grid", "hybrid", "bayes"],
+                   help="grid (exhaustive), hybrid (grid+Nelder-Mead), bayes (Bayesian/GP)")
+    p.add_argument("--refine", action="store_true", help="[hybrid only] Apply Nelder-Mead refinement after grid search")
+    p.add_argument("--n-calls", type=int, default=50, help="[bayes only] Total number of evaluations")
+    p.add_argument("--n-initial", type=int, default=10, help="[bayes only] Random evaluations before GP fitting")
+    p.add_argument("--random-state", type=int, default=None, help="[bayes only] Random seed for reproducibility")
+    p.add_argument("--objective", choices=["slice2d", "volume3d"], default="slice2d",
+                   help="slice2d: the reference's z=0 slice objective; volume3d: |E-| of compute_energy_3d")
+    p.add_argument("--out", type=str, default="results/optimization.json")
+    args = p.parse_args(argv)
+
+    print(f"Running optimization over sigma in [{args.sigma_min}, {args.sigma_max}], v in [{args.v_min}, {args.v_max}]"
+          f" ({args.objective} objective)")
+    common = dict(rho=args.rho, sigma_range=(args.sigma_min, args.sigma_max), v_range=(args.v_min, args.v_max),
+                  extent=args.extent, n=args.n, objective=args.objective)
+    if args.method == "bayes":
+        print(f"  Bayesian optimization (GP): {args.n_calls} total calls ({args.n_initial} initial random)")
+        result = opt.optimize_bayesian(n_calls=args.n_calls, n_initial_points=args.n_initial,
+                                       random_state=args.random_state, **common)
+    else:
+        refine = args.refine and args.method == "hybrid"
+        print(f"  Grid search: {args.sigma_steps} x {args.v_steps} = {args.sigma_steps * args.v_steps} evaluations"
+              + ("; then Nelder-Mead local refinement" if refine else ""))
+        result = opt.optimize_hybrid(sigma_steps=args.sigma_steps, v_steps=args.v_steps, refine=refine, **common)
+    params = {"rho": args.rho, "extent": args.extent, "n": args.n, "sigma_range": [args.sigma_min, args.sigma_max],
+              "v_range": [args.v_min, args.v_max], "method": args.method, "objective": args.objective}
+    if args.method == "bayes":
+        params.update(n_calls=args.n_calls, n_initial=args.n_initial)
+        if args.random_state is not None:
+            params["random_state"] = args.random_state
+    else:
+        params.update(sigma_steps=args.sigma_steps, v_steps=args.v_steps)
+        if args.method == "hybrid":
+            params["refine"] = args.refine
+    payload = {"git": _git_info(), "params": params,
+               "optimization": {"best_params": {k: float(v) for k, v in result.best_params.items()},
+                                "best_value": float(result.best_value),
+                                "initial_params": {k: float(v) for k, v in result.initial_params.items()},
+                                "initial_value": float(result.initial_value), "n_evaluations": int(result.n_evaluations),
+                                "success": bool(result.success), "method": result.method, "message": str(result.message)}}
+    _write_json(args.out, payload)
+    print(f"Optimization complete: best |E-| = {result.best_value:.6e} at sigma = {result.best_params['sigma']:.4f}, "
+          f"v = {result.best_params['v']:.4f} ({result.n_evaluations} evaluations, {result.method}); saved to {args.out}")
+    return 0
+
+
+def convergence_main(argv=None) -> int:
+    """``scripts/convergence_study_3d.py`` (/root/reference/scripts/convergence_study_3d.py:21-183) on the engine: one
+    ``reproduce`` run per resolution, each leaving ``convergence_runs/repro_n{n}.json`` beside ``--out`` as the reference's
+    subprocess loop does (here in-process: the engine handle is created once), then the same table and summary JSON."""
+    p = argparse.ArgumentParser(description="3D convergence study on the B200 engine")
+    p.add_argument("--mode", default="3d", choices=["3d"])
+    p.add_argument("--backend", default="b200", choices=["b200"])
+    p.add_argument("--dtype", default="float64", choices=["float64", "float32"])
+    p.add_argument("--n-values", type=str, default="40,60,80,100", help="Comma-separated list of grid resolutions")
+    p.add_argument("--rho", type=float, default=5.0)
+    p.add_argument("--sigma", type=float, default=4.0)
+    p.add_argument("--v", type=float, default=1.0)
+    p.add_argument("--out", type=str, required=True)
+    args = p.parse_args(argv)
+    n_values = [int(t.strip()) for t in args.n_values.split(",")]
+    out_dir = os.path.join(os.path.dirname(args.out) or ".", "convergence_runs")
+    os.makedirs(out_dir, exist_ok=True)
+    started = time.perf_counter()
+    results = []
+    for n in n_values:
+        out_path = os.path.join(out_dir, f"repro_n{n}.json")
+        t0 = time.perf_counter()
+        reproduce_main(["--mode", args.mode, "--backend", args.backend, "--dtype", args.dtype, "--n", str(n),
+                        "--rho", str(args.rho), "--sigma", str(args.sigma), "--v", str(args.v), "--out", out_path])
+        elapsed = time.perf_counter() - t0
+        with open(out_path) as f:
+            data = json.load(f)
+        tail = data["tail_2pt"]["at_inf"]
+        results.append({"n": n, "n_points": n ** 3, "e_pos_inf": tail["e_pos"], "e_neg_inf": tail["e_neg"],
+                        "e_net_inf": tail["e_net"], "e_abs_inf": tail["e_abs"], "neg_fraction": tail["neg_fraction"],
+                        "net_over_abs_pct": tail["net_over_abs"] * 100,
+                        "ratio_r2": data["tail_2pt"]["at_r2"]["ratio_e_pos_over_abs_e_neg"],
+                        "wall_clock_s": elapsed, "kernel_ms": data["run"]["engine"]["kernel_ms"], "file": out_path})
+    total_time = time.perf_counter() - started
+    print("=" * 72)
+    print(f"{'n':>6} {'Points':>13} {'|E_net/E_abs|%':>15} {'Ratio(R2)':>12} {'Time(s)':>10} {'kernel ms':>10}")
+    print("-" * 72)
+    for r in results:
+        print(f"{r['n']:>6} {r['n_points']:>13,} {abs(r['net_over_abs_pct']):>15.6f} {r['ratio_r2']:>12.5f} "
+              f"{r['wall_clock_s']:>10.3f} {r['kernel_ms']:>10.3f}")
+    print("=" * 72)
+    payload = {"meta": {"timestamp_utc": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "python": sys.version},
+               "params": {"mode": args.mode, "backend": args.backend, "dtype": args.dtype, "rho": args.rho,
+                          "sigma": args.sigma, "v": args.v},
+               "results": results, "total_time_s": total_time}
+    _write_json(args.out, payload)
+    print(f"Results written to: {args.out}  (total {total_time:.1f}s)")
+    return 0
+
+
 def main(argv=None) -> int:
     argv = sys.argv[1:] if argv is None else argv
+    if argv and argv[0] == "optimize":
+        return optimize_main(argv[1:])
+    if argv and argv[0] == "convergence":
+        return convergence_main(argv[1:])
     if argv and argv[0] == "reproduce":
         return reproduce_main(argv[1:])
     if argv and argv[0] == "sweep":
         return sweep_main(argv[1:])
     if argv and argv[0] == "slice":
         return slice_main(argv[1:])
-    print("usage: python -m irrotational_warp_lab_b200.cli {reproduce|sweep|slice} [options]", file=sys.stderr)
+    print("usage: python -m irrotational_warp_lab_b200.cli {reproduce|sweep|slice|optimize|convergence} [options]", file=sys.stderr)
     return 2
 
 

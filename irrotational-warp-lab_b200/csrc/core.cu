@@ -260,6 +260,12 @@ int iwb_destroy(iwb_handle* h)
 {
     if (!h) return IWB_OK;
     cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (int s = 0; s < NASYNC; ++s) {
+        AsyncSlot& a = h->aslot[s];
+        a.h_coords.release(); a.coords.release(); a.partial.release(); a.counter.release();
+        if (a.done) cudaEventDestroy(a.done);
+    }
     for (int s = 0; s < NSCRATCH; ++s) {
         Scratch& c = h->scr[s];
         if (c.stream) cudaStreamSynchronize(c.stream);

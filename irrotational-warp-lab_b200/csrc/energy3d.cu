@@ -19,6 +19,7 @@ namespace iwb {
 static cudaError_t launch_k3(int dtype, int mode, int nshell, bool emit, int cfg, const K3Params& P, int sm_count, cudaStream_t st)
 {
     if (mode == IWB_MODE_FAST) return launch_k3_fast(nshell, emit, cfg, P, sm_count, st);
+    if (dtype == IWB_F32_STRICT) return launch_k3_f32strict(nshell, emit, cfg, P, sm_count, st);
     if (dtype == IWB_F64)
         return emit ? launch_nsh<IWB_F64, true, 0>(nshell, cfg, P, sm_count, st)
                     : launch_nsh<IWB_F64, false, 0>(nshell, cfg, P, sm_count, st);
@@ -29,8 +30,10 @@ static cudaError_t launch_k3(int dtype, int mode, int nshell, bool emit, int cfg
 static int validate(const iwb_params3d* p)
 {
     if (!p) return fail(IWB_ERR_INVALID, "params is NULL");
-    if (p->dtype != IWB_F64 && p->dtype != IWB_F32_REF)
-        return fail(IWB_ERR_INVALID, "energy3d: dtype must be IWB_F64 or IWB_F32_REF (IWB_F32_STRICT is not built yet)");
+    if (p->dtype != IWB_F64 && p->dtype != IWB_F32_REF && p->dtype != IWB_F32_STRICT)
+        return fail(IWB_ERR_INVALID, "energy3d: dtype must be IWB_F64, IWB_F32_REF or IWB_F32_STRICT");
+    if (p->dtype == IWB_F32_STRICT && !(isfinite((float)p->sinh_rs) && isfinite((float)p->cosh_rs)))
+        return fail(IWB_ERR_INVALID, "energy3d: IWB_F32_STRICT needs sinh(rho*sigma) finite in float32 (rho*sigma < 88)");
     if (p->mode != IWB_MODE_EXACT && p->mode != IWB_MODE_FAST) return fail(IWB_ERR_INVALID, "energy3d: unknown mode");
     if (p->mode == IWB_MODE_FAST && p->dtype != IWB_F64)
         return fail(IWB_ERR_INVALID, "energy3d: IWB_MODE_FAST exists for IWB_F64 only");
@@ -210,6 +213,37 @@ static int enqueue_slab(iwb_handle* h, Scratch& c, const iwb_params3d* p, double
     return launch_slab(h, L, table, st, tiles_out);
 }
 
+// Non-blocking launch with its own staging slot (see AsyncSlot): no stream synchronisation, safe across streams.
+static int acquire_aslot(iwb_handle* h, AsyncSlot** out)
+{
+    AsyncSlot& a = h->aslot[h->next_aslot];
+    h->next_aslot = (h->next_aslot + 1) % NASYNC;
+    if (!a.done) IWB_CUDA(cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming));
+    if (a.in_flight) {
+        IWB_CUDA(cudaEventSynchronize(a.done));      // only when NASYNC launches are still in flight
+        a.in_flight = false;
+    }
+    *out = &a;
+    return IWB_OK;
+}
+
+static int enqueue_slab_async(iwb_handle* h, const iwb_params3d* p, double* table, cudaStream_t st, double* rho_dev,
+                              bool tiles_out, Launch3* L_out = nullptr, AsyncSlot** slot_out = nullptr)
+{
+    AsyncSlot* a = nullptr;
+    int rc = acquire_aslot(h, &a);
+    if (rc) return rc;
+    Launch3 L;
+    rc = prepare_slab(h, p, a->h_coords, a->coords, a->partial, a->counter, st, rho_dev, &L);
+    if (rc) return rc;
+    if (L_out) { *L_out = L; *slot_out = a; return IWB_OK; }       // the caller launches (and records the event) itself
+    rc = launch_slab(h, L, table, st, tiles_out);
+    if (rc) return rc;
+    IWB_CUDA(cudaEventRecord(a->done, st));
+    a->in_flight = true;
+    return IWB_OK;
+}
+
 static void unpack_row(const double* row, int nshell, iwb_result* out)
 {
     auto as_i64 = [](double d) { int64_t v; memcpy(&v, &d, 8); return v; };
@@ -286,6 +320,18 @@ __global__ void k_selftest_phi(PhiConst pc, double lo, double hi, uint64_t count
 
 }  // namespace iwb
 
+constexpr size_t PEER_HEADER_BYTES = 512;      // flags [2][PEER_MAX] of 8 bytes = 256, padded
+struct iwb_peer {
+    iwb_handle* h = nullptr;
+    int rank = 0, world = 1, nfb_max = 0;
+    size_t buf_doubles = 0;
+    void* base[iwb::PEER_MAX] = {};              // flags + two gathered buffers of every rank (own: cudaMalloc, others: IPC-mapped)
+    bool opened[iwb::PEER_MAX] = {};
+    bool connected = false;
+    double* table = nullptr;                     // [nfb_max][ROW] scratch + the ticket word
+    unsigned long long epoch = 0;
+};
+
 struct iwb_plan3d {
     iwb_handle* h = nullptr;
     iwb::Launch3 L;
@@ -328,11 +374,7 @@ int iwb_energy3d_slab_async(iwb_handle* h, const iwb_params3d* p, double* table_
         return fail(IWB_ERR_INVALID, "iwb_energy3d_slab_async: rho_out must be a device pointer");
     if (p->tile_stride > 1) return fail(IWB_ERR_INVALID, "iwb_energy3d_slab_async: tile shards go through iwb_energy3d_tiles_async");
     IWB_CUDA(cudaSetDevice(h->device));
-    Scratch& c = h->scr[0];
-    cudaStream_t st = (cudaStream_t)stream;      // NULL is CUDA's default stream
-    // the staging buffer of scratch 0 is reused: make sure the previous upload from it has completed
-    IWB_CUDA(cudaStreamSynchronize(st));
-    return enqueue_slab(h, c, p, table_device, st, p->rho_out);
+    return enqueue_slab_async(h, p, table_device, (cudaStream_t)stream /* NULL is CUDA's default stream */, p->rho_out, false);
 }
 
 int iwb_reduce_table(iwb_handle* h, const double* table_device, int nrows, int nshell, void* stream, iwb_result* out)
@@ -439,10 +481,149 @@ int iwb_energy3d_tiles_async(iwb_handle* h, const iwb_params3d* p, double* chain
     if (rc) return rc;
     if (p->rho_out) return fail(IWB_ERR_INVALID, "iwb_energy3d_tiles_async: rho_out must be NULL");
     IWB_CUDA(cudaSetDevice(h->device));
+    return enqueue_slab_async(h, p, chains_device, (cudaStream_t)stream /* NULL is CUDA's default stream */, nullptr, true);
+}
+
+int iwb_read_row(iwb_handle* h, const double* row_device, int nshell, void* stream, iwb_result* out)
+{
+    if (!h || !row_device || !out) return fail(IWB_ERR_INVALID, "iwb_read_row: null argument");
+    if (nshell < 0 || nshell > IWB_MAX_SHELLS) return fail(IWB_ERR_INVALID, "iwb_read_row: nshell out of range");
+    IWB_CUDA(cudaSetDevice(h->device));
     Scratch& c = h->scr[0];
-    cudaStream_t st = (cudaStream_t)stream;      // NULL is CUDA's default stream
-    IWB_CUDA(cudaStreamSynchronize(st));         // the staging buffer of scratch 0 is reused
-    return enqueue_slab(h, c, p, chains_device, st, nullptr, true);
+    cudaStream_t st = (cudaStream_t)stream;
+    IWB_CUDA(c.h_out.reserve(ROW_BYTES_MIN));
+    IWB_CUDA(cudaMemcpyAsync(c.h_out.p, row_device, ROW_BYTES_MIN, cudaMemcpyDeviceToHost, st));
+    IWB_CUDA(cudaStreamSynchronize(st));
+    memset(out, 0, sizeof(*out));
+    unpack_row((const double*)c.h_out.p, nshell, out);
+    return IWB_OK;
+}
+
+// ---- peer exchange: the chain sums of the tile-shard path cross NVLink as plain stores (no NCCL launch) ---------------
+int iwb_peer_create(iwb_handle* h, int rank, int world, int nfb_max, iwb_peer** out, void* handle_out)
+{
+    if (!h || !out || !handle_out) return fail(IWB_ERR_INVALID, "iwb_peer_create: null argument");
+    *out = nullptr;
+    if (!(world == 1 || world == 2 || world == 4 || world == 8 || world == 16) || rank < 0 || rank >= world)
+        return fail(IWB_ERR_INVALID, "iwb_peer_create: world must be 1, 2, 4, 8 or 16 and 0 <= rank < world");
+    if (nfb_max < 1) return fail(IWB_ERR_INVALID, "iwb_peer_create: nfb_max must be >= 1");
+    IWB_CUDA(cudaSetDevice(h->device));
+    iwb_peer* pr = new iwb_peer();
+    pr->h = h; pr->rank = rank; pr->world = world; pr->nfb_max = nfb_max;
+    pr->buf_doubles = (size_t)nfb_max * IWB_TILE_CHAINS * ROW;          // [S][nfb][NCH / S][ROW]
+    const size_t bytes = PEER_HEADER_BYTES + 2 * pr->buf_doubles * sizeof(double);
+    cudaError_t e = cudaMalloc(&pr->base[rank], bytes);
+    if (e == cudaSuccess) e = cudaMemset(pr->base[rank], 0, bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pr->table, ((size_t)nfb_max * ROW + 32) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(pr->table, 0, ((size_t)nfb_max * ROW + 32) * sizeof(double));
+    cudaIpcMemHandle_t hd;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&hd, pr->base[rank]);
+    if (e != cudaSuccess) {
+        if (pr->base[rank]) cudaFree(pr->base[rank]);
+        if (pr->table) cudaFree(pr->table);
+        delete pr;
+        return fail(IWB_ERR_CUDA, std::string("iwb_peer_create: ") + cudaGetErrorString(e));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == IWB_PEER_HANDLE_BYTES, "IPC handle size");
+    memcpy(handle_out, &hd, sizeof(hd));
+    *out = pr;
+    return IWB_OK;
+}
+
+int iwb_peer_connect(iwb_peer* pr, const void* all_handles)
+{
+    if (!pr || !all_handles) return fail(IWB_ERR_INVALID, "iwb_peer_connect: null argument");
+    IWB_CUDA(cudaSetDevice(pr->h->device));
+    for (int r = 0; r < pr->world; ++r) {
+        if (r == pr->rank) continue;
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char*)all_handles + (size_t)r * IWB_PEER_HANDLE_BYTES, sizeof(hd));
+        IWB_CUDA(cudaIpcOpenMemHandle(&pr->base[r], hd, cudaIpcMemLazyEnablePeerAccess));
+        pr->opened[r] = true;
+    }
+    pr->connected = true;
+    return IWB_OK;
+}
+
+int iwb_debug_peer_connect_local(iwb_peer* pr, iwb_peer* const* all_peers)
+{
+    if (!pr || !all_peers) return fail(IWB_ERR_INVALID, "iwb_debug_peer_connect_local: null argument");
+    for (int r = 0; r < pr->world; ++r) {
+        if (!all_peers[r] || all_peers[r]->world != pr->world || all_peers[r]->rank != r || all_peers[r]->nfb_max != pr->nfb_max)
+            return fail(IWB_ERR_INVALID, "iwb_debug_peer_connect_local: peers do not form one group");
+        if (r != pr->rank) pr->base[r] = all_peers[r]->base[r];
+    }
+    pr->connected = true;
+    return IWB_OK;
+}
+
+int iwb_peer_destroy(iwb_peer* pr)
+{
+    if (!pr) return IWB_OK;
+    cudaSetDevice(pr->h->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < pr->world; ++r)
+        if (pr->opened[r]) cudaIpcCloseMemHandle(pr->base[r]);
+    if (pr->base[pr->rank]) cudaFree(pr->base[pr->rank]);
+    if (pr->table) cudaFree(pr->table);
+    delete pr;
+    return IWB_OK;
+}
+
+// k_energy3d of launch record L, then the push of the chain sums into every rank's gathered buffer and the combine
+static int launch_exchange(iwb_handle* h, iwb_peer* pr, const Launch3& L, int nfb, cudaStream_t st, double* row_device)
+{
+    const int S = pr->world, first = pr->rank;
+    if (L.P.nspans > 0) {
+        cudaError_t e = launch_k3(L.dtype, L.mode, L.nshell, L.emit, L.cfg_id, L.P, h->sm_count, st);
+        if (e != cudaSuccess) return fail(IWB_ERR_CUDA, std::string("k_energy3d launch: ") + cudaGetErrorString(e));
+    }
+    const unsigned long long epoch = ++pr->epoch;
+    const int par = (int)(epoch & 1ull);
+    ExchParams X;
+    memset(&X, 0, sizeof(X));
+    for (int r = 0; r < S; ++r) {
+        char* b = (char*)pr->base[r];
+        X.peers.flag[r] = (unsigned long long*)(b + (size_t)par * PEER_MAX * sizeof(unsigned long long));
+        X.peers.gath[r] = (double*)(b + PEER_HEADER_BYTES) + (size_t)par * pr->buf_doubles;
+    }
+    X.gath_local = X.peers.gath[pr->rank];
+    X.flag_local = X.peers.flag[pr->rank];
+    X.epoch = epoch; X.rank = pr->rank; X.stride = S; X.nfb = nfb;
+    X.table = pr->table; X.row = row_device;
+    X.ticket = (unsigned int*)(pr->table + (size_t)pr->nfb_max * ROW);
+    k_chain_sums_push<<<nfb, 32 * (IWB_TILE_CHAINS / S), 0, st>>>(L.P.partial, X.peers, 0, nfb, L.ntiles, first, S,
+                                                                  IWB_TILE_CHAINS, L.P.counter);
+    k_exchange_combine<<<nfb, 32 * IWB_TILE_CHAINS, 0, st>>>(X);
+    IWB_CUDA(cudaGetLastError());
+    return IWB_OK;
+}
+
+int iwb_energy3d_tiles_exchange_async(iwb_handle* h, iwb_peer* pr, const iwb_params3d* p, void* stream, double* row_device)
+{
+    if (!h || !pr || !row_device) return fail(IWB_ERR_INVALID, "iwb_energy3d_tiles_exchange_async: null argument");
+    int rc = validate(p);
+    if (rc) return rc;
+    if (!pr->connected) return fail(IWB_ERR_INVALID, "iwb_energy3d_tiles_exchange_async: iwb_peer_connect has not been called");
+    if (p->rho_out) return fail(IWB_ERR_INVALID, "iwb_energy3d_tiles_exchange_async: rho_out must be NULL");
+    const int S = p->tile_stride > 1 ? p->tile_stride : 1, first = p->tile_stride > 1 ? p->tile_first : 0;
+    if (S != pr->world || first != pr->rank)
+        return fail(IWB_ERR_INVALID, "iwb_energy3d_tiles_exchange_async: tile_stride / tile_first must be the group's world size / this rank");
+    if (p->i_begin != 0 || p->i_end != p->n0)
+        return fail(IWB_ERR_INVALID, "iwb_energy3d_tiles_exchange_async: a tile shard covers the whole of axis 0");
+    const int nfb = (p->n0 + FLUSH - 1) / FLUSH;
+    if (nfb > pr->nfb_max) return fail(IWB_ERR_INVALID, "iwb_energy3d_tiles_exchange_async: grid has more flush blocks than the peer buffers hold");
+    IWB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Launch3 L;
+    AsyncSlot* a = nullptr;
+    rc = enqueue_slab_async(h, p, nullptr, st, nullptr, true, &L, &a);
+    if (rc) return rc;
+    rc = launch_exchange(h, pr, L, nfb, st, row_device);
+    if (rc) return rc;
+    IWB_CUDA(cudaEventRecord(a->done, st));
+    a->in_flight = true;
+    return IWB_OK;
 }
 
 int iwb_reduce_chains(iwb_handle* h, const double* gathered_device, int tile_stride, int nfb, int nshell, void* stream,
@@ -584,6 +765,19 @@ int iwb_plan3d_run_async(iwb_plan3d* plan, double* table_device, void* stream)
     IWB_CUDA(cudaSetDevice(plan->h->device));
     cudaStream_t st = (cudaStream_t)stream;      // NULL is CUDA's default stream
     return launch_slab(plan->h, plan->L, table_device, st, plan->L.tile_stride > 1);
+}
+
+int iwb_plan3d_run_exchange_async(iwb_plan3d* plan, iwb_peer* pr, void* stream, double* row_device)
+{
+    if (!plan || !pr || !row_device) return fail(IWB_ERR_INVALID, "iwb_plan3d_run_exchange_async: null argument");
+    if (!pr->connected) return fail(IWB_ERR_INVALID, "iwb_plan3d_run_exchange_async: iwb_peer_connect has not been called");
+    const Launch3& L = plan->L;
+    if (L.tile_stride != pr->world || L.tile_first != pr->rank || L.P.i_begin != 0 || L.P.i_end != L.P.n0)
+        return fail(IWB_ERR_INVALID, "iwb_plan3d_run_exchange_async: the plan is not this rank's tile shard of the group");
+    const int nfb = (L.P.n0 + FLUSH - 1) / FLUSH;
+    if (nfb > pr->nfb_max) return fail(IWB_ERR_INVALID, "iwb_plan3d_run_exchange_async: grid has more flush blocks than the peer buffers hold");
+    IWB_CUDA(cudaSetDevice(plan->h->device));
+    return launch_exchange(plan->h, pr, L, nfb, (cudaStream_t)stream, row_device);
 }
 
 int iwb_plan3d_destroy(iwb_plan3d* plan)

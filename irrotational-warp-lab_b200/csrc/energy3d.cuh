@@ -50,9 +50,9 @@
 #endif
 
 #ifndef IWB_SUM_RHO
-#define IWB_SUM_RHO 1       // tally rho and multiply by dV at the flush: one DMUL per point less (+0.25 % on B200); the sums
-                            // move in the last bit (bar: 1e-10), the signs are those of rho (dV > 0); needs IWB_TALLY == 2
-                            // for exact zero counts when rho * dV underflows
+#define IWB_SUM_RHO 0       // 1: tally rho and multiply by dV at the flush: one DMUL per point less, +0.8 % on B200
+                            // (profiles/r2_ab3_tally_nbsync.log).  NOT adopted: the reference classifies e = rho * dV, and a
+                            // rho whose product with dV underflows would be counted with its sign instead of as a zero
 #endif
 #ifndef IWB_OC_UNROLL
 #define IWB_OC_UNROLL 1     // both rows of the O + C loop unrolled: no loop overhead, row b's loads overlap row a's tally (+0.9 %)
@@ -61,20 +61,30 @@
 #define IWB_P4 1       // task P evaluates both rows of a warp at once: four independent phi evaluations per thread
 #endif
 #ifndef IWB_JFACE
-#define IWB_JFACE 1    // tiles at the two j faces hold RJ - 2 output rows (no halo beyond the face), as the k-face tiles hold
-                       // RK - 2 columns: n = 256 is 7 instead of 8 tile rows, n = 400 11 instead of 12
+#define IWB_JFACE 0    // 1: tiles at the two j faces hold RJ - 2 output rows (no halo beyond the face), as the k-face tiles hold
+                       // RK - 2 columns: n = 256 is 7 instead of 8 tile rows, n = 400 11 instead of 12.  Measured on B200
+                       // (profiles/r2_ab2_tally_jface.log): n = 256 / 400 +2 %, n = 1024 -4 % (the row offset costs the hot
+                       // loops registers), so it is off; round 1 saw the same with its own version.
 #endif
 #ifndef IWB_TALLY
-#define IWB_TALLY 2    // 1: round-1 tally (two FP64 compares per point, per-row shell test from sxy + zzmin)
-                       // 2: integer sign count with a rare path for zero / NaN / inf, per-tile row tables for the shell
-                       //    tests (skip / fully inside / mixed), pair sums
+#define IWB_TALLY 3    // 1: round-1 tally (two FP64 compares per point, per-row shell test from (x*x + y*y) + zz_min)
+                       // 3: + "row outside every shell" from a per-tile table of x*x limits (two additions per row less)
+                       // 4: integer sign count with an exact rare path for zero / NaN / inf instead of the FP64 compares
+                       // 2: 3 + 4 + "row fully inside shell s" tables with pair sums
+                       // B200, n = 1024^3 (profiles/r2_ab2_tally_jface.log, r2_ab3_tally_nbsync.log): 1: 114.2, 3: 115.5,
+                       // 4: 113.0, 2: 113.4 Gpoints/s -- the variants that issue fewer instructions are not the faster ones
 #endif
-#if !IWB_FLUSH_PACK && IWB_TALLY == 2
+#define IWB_T_INT (IWB_TALLY == 2 || IWB_TALLY == 4)    // integer sign count + exact rare path (zero / NaN / inf), positives derived
+#define IWB_T_SKIP (IWB_TALLY == 2 || IWB_TALLY == 3)   // "row outside every shell" from a per-tile table instead of two additions per row
+#define IWB_T_IN (IWB_TALLY == 2)                        // "row fully inside shell s" tables + pair sums
+#if !IWB_FLUSH_PACK && IWB_T_INT
 #error "IWB_TALLY == 2 derives the positive count in the packed flush only"
 #endif
 #ifndef IWB_NBSYNC
-#define IWB_NBSYNC 0   // 1: the march synchronises each warp with its two row neighbours only (progress counters in shared
-                       // memory) instead of one CTA-wide mbarrier phase per plane; 2: same with a relaxed flag store
+#define IWB_NBSYNC 0   // neighbour-only synchronisation of the march instead of one CTA-wide mbarrier phase per plane:
+                       // 1 / 2: progress counters in shared memory (release / volatile stores); 3: two mbarriers per warp.
+                       // Measured on B200 at n = 1024^3: 0: 113.3 / 114.2, 1: 108.8, 2: 109.0, 3: 111.8 Gpoints/s -- the
+                       // CTA-wide split barrier is the fastest (profiles/r2_ab1_*.log, r2_ab3_*.log); kept for the record
 #endif
 #ifndef IWB_DBG
 #define IWB_DBG 0      // development only: 1 = skip task O, 2 = skip the phi evaluation, 3 = both
@@ -162,7 +172,7 @@ struct Geo {
     static constexpr int TJ_MAX = RJ - 4;
     static constexpr int NT = NW * 32;
     static constexpr int SCRATCH = NW * ROW;     // block-reduction scratch (doubles)
-    static constexpr int NROWTAB = (IWB_TALLY == 2) ? 4 : 1;     // per-row tables: y*y [, x*x limits: outside all shells, inside shell 0, 1]
+    static constexpr int NROWTAB = IWB_T_IN ? 4 : (IWB_T_SKIP ? 2 : 1);     // per-row tables: y*y [, x*x limits: outside all shells, inside shell 0, 1]
     static constexpr size_t SMEM_BYTES = (size_t(NPLANES) * PLANE + SMEM_PAD_FRONT + SMEM_PAD + NROWTAB * RJ + SCRATCH + NEDGE) * sizeof(double);
 };
 
@@ -211,7 +221,39 @@ k_energy3d(const __grid_constant__ K3Params P)
         ec_s[threadIdx.x] = (&P.cx.h2)[8 * axis + 2 + q];
     }
     __syncthreads();
-#if IWB_NBSYNC
+#if IWB_NBSYNC == 3
+    // Neighbour synchronisation with hardware waits: every warp owns TWO mbarriers (even / odd steps, 32 arrivals each);
+    // after O(i) + C(i+1) of step t it arrives on its barrier t & 1, and before step t + 1 it waits for phase t >> 1 of
+    // both row neighbours' barrier t & 1.  A neighbour cannot arrive at step t + 2 (the next phase of the same barrier)
+    // before this warp has arrived at step t + 1, so the parity is unambiguous.  Entry 0 / NW + 1 of each row mirror the
+    // warps NW - 1 / 0 (those two warps arrive twice), which puts the neighbours at -+ 8 bytes of the own entry.
+    __shared__ unsigned long long s_nb[2][NW + 2];
+    static_assert(RJ == 2 * NW, "row neighbours are the warps w -+ 1 only when every warp owns the rows w and w + NW");
+    if (threadIdx.x < 2 * (NW + 2))
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_nb[0][0] + threadIdx.x)), "r"(32));
+    __syncthreads();
+    unsigned nb_step = 0;                                  // march steps completed (same on all lanes)
+    const unsigned nb_me = keep_u32((unsigned)__cvta_generic_to_shared(&s_nb[0][1 + ty]));
+    constexpr int NB_ROW = (NW + 2) * 8;                   // bytes from a warp's even barrier to its odd one
+    auto step_arrive = [&]() {
+        const unsigned a = nb_me + (nb_step & 1u) * NB_ROW;
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+        if (ty == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+%1];" ::"r"(a), "n"(8 * NW) : "memory");
+        if (ty == NW - 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+%1];" ::"r"(a), "n"(-8 * NW) : "memory");
+    };
+    auto step_wait = [&]() {
+        const unsigned a = nb_me + (nb_step & 1u) * NB_ROW, par = (nb_step >> 1) & 1u;
+        unsigned done;
+        for (;;) {
+            asm volatile("{ .reg .pred p, q; mbarrier.try_wait.parity.shared::cta.b64 p, [%1+-8], %2; "
+                         "mbarrier.try_wait.parity.shared::cta.b64 q, [%1+8], %2; and.pred p, p, q; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(a), "r"(par) : "memory");
+            if (__all_sync(0xffffffffu, done != 0u)) break;
+            __nanosleep(IWB_BARRIER_BACKOFF_NS);
+        }
+        ++nb_step;
+    };
+#elif IWB_NBSYNC
     // Neighbour synchronisation of the march.  Every cross-warp dependency of a step runs between ROW neighbours: O(i)
     // reads phi_x(i), phi_y(i) of the rows j -+ 1, C(i+1) reads phi(i+1) of the rows j -+ 1; columns k -+ 1 belong to the
     // warp itself, the x direction to the thread itself.  Warp w owns the rows w and w + NW, so its neighbours are the
@@ -347,13 +389,13 @@ k_energy3d(const __grid_constant__ K3Params P)
             for (int off = 16; off > 0; off >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, off));
             zzmin_s = m;
         }
-#if IWB_TALLY == 2
+        constexpr int NIN = (IWB_T_IN && NSH >= 1 && NSH <= 2) ? NSH : 0;     // shells with a "row fully inside" table
+#if IWB_T_INT || IWB_T_SKIP
         // hi-word OR-masks that make a non-output column look like 1.0 to the special-value test of the tally, and the
         // number of output columns of this lane
         const int fx0 = (int)keep_u32((cf0 & 16u) ? 0u : 0x3ff00000u), fx1 = (int)keep_u32((cf1 & 16u) ? 0u : 0x3ff00000u);
         const int npl = (int)((cf0 >> 4) & 1u) + (int)((cf1 >> 4) & 1u);
-        constexpr int NIN = (NSH >= 1 && NSH <= 2) ? NSH : 0;     // shells with a "row fully inside" table
-        if (NSH > 0) {
+        if (NSH > 0 && IWB_T_SKIP) {
             // Row tables of the shell tests.  s = RN(RN(x*x + y*y) + z*z) is monotone in each term, so for a row (fixed y)
             // of this tile:  x*x > xout[row]  =>  even the column with the smallest z*z lies outside the largest shell;
             //                x*x <= xin[s][row]  =>  even the column with the largest z*z lies inside shell s.
@@ -397,19 +439,25 @@ k_energy3d(const __grid_constant__ K3Params P)
         // Counts: every point is exactly one of neg / pos / zero / NaN; the first three are counted here in 8-bit
         // fields of one register (<= 64 points per thread and flush interval), NaN is derived by the host.  The zero
         // field also counts the masked non-output columns; the flush subtracts their (known) number.
-#if IWB_TALLY == 2
-        // Pair sums first (e0 + e1, |e0| + |e1|): the main accumulators and every shell the row lies fully inside take the
-        // same two values.  Counts: the sign bit of the masked value counts the negative points; a point whose high word
-        // says zero / denormal / inf / NaN sends its thread through an exact, rare path that counts zeros and NaNs and
-        // takes the sign count back where it does not apply (-0.0, -NaN); positives are derived at the flush.  cnt3
-        // fields: negative | NaN << 8 | zero << 16.
+        // IWB_T_IN: pair sums first (e0 + e1, |e0| + |e1|): the main accumulators and every shell the row lies fully inside
+        // take the same two values.  IWB_T_INT: the sign bit of the masked value counts the negative points; a point whose
+        // high word says zero / tiny / inf / NaN sends its thread through an exact, rare path that counts zeros and NaNs
+        // and takes the sign count back where it does not apply (-0.0, -NaN); positives are derived at the flush
+        // (cnt3 fields: negative | NaN << 8 | zero << 16).
         auto tally2 = [&](const double (&e)[2], unsigned ya, double xxi) {
             const int h0 = __double2hiint(e[0]), h1 = __double2hiint(e[1]);
             const int hm0 = h0 & om0, hm1 = h1 & om1;
             const double em0 = __hiloint2double(hm0, __double2loint(e[0]) & om0);
             const double em1 = __hiloint2double(hm1, __double2loint(e[1]) & om1);
-            const double t = em0 + em1, ta = fabs(em0) + fabs(em1);
-            acc_sum += t; acc_abs += ta;
+            double t = 0.0, ta = 0.0;
+            if (IWB_T_IN) {
+                t = em0 + em1; ta = fabs(em0) + fabs(em1);
+                acc_sum += t; acc_abs += ta;
+            } else {
+                acc_sum += em0; acc_abs += fabs(em0);
+                acc_sum += em1; acc_abs += fabs(em1);
+            }
+#if IWB_T_INT
             cnt3 += (int)((unsigned)hm0 >> 31) + (int)((unsigned)hm1 >> 31);
             // |value| < 2^-511 (zero, denormal, or so small that value * dV may underflow when rho is tallied) or exponent
             // all ones (inf, NaN), at an output column: classify exactly what the reference classifies, e = rho * dV
@@ -427,9 +475,27 @@ k_energy3d(const __grid_constant__ K3Params P)
                     else if (ev != ev) cnt3 += 0x100 - (int)((unsigned)hm1 >> 31);
                 }
             }
+#else
+            // every point is exactly one of neg / pos / zero / NaN; the zero field also counts the masked columns
+            if (em0 < 0.0) cnt3 += 1;
+            if (em1 < 0.0) cnt3 += 1;
+            if (em0 > 0.0) cnt3 += 0x100;
+            if (em1 > 0.0) cnt3 += 0x100;
+            if (((hm0 & 0x7fffffff) | __double2loint(em0)) == 0) cnt3 += 0x10000;
+            if (((hm1 & 0x7fffffff) | __double2loint(em1)) == 0) cnt3 += 0x10000;
+#endif
             if (NSH > 0) {
                 constexpr int RB = RJ * 8;
-                if (xxi > lds_f64<RB>(ya)) return;          // no column of this row inside any shell (warp-uniform)
+                double yyj = 0.0;
+                if (IWB_T_SKIP) {
+                    if (xxi > lds_f64<RB>(ya)) return;          // no column of this row inside any shell (warp-uniform)
+                } else {
+                    // s = RN(sxy + zz) is monotone in zz: if even the tile's smallest zz lies outside the largest shell, no
+                    // column of this row is inside any shell (all lanes agree: uniform branch)
+                    yyj = lds_f64<0>(ya);
+                    if (DT == IWB_F64) { if ((xxi + yyj) + zzmin_s > P.shell_thr_max) return; }
+                    else if (__fadd_rn(__fadd_rn((float)xxi, (float)yyj), (float)zzmin_s) > (float)P.shell_thr_max) return;
+                }
                 bool row_in[NSHA];
                 bool mixed = false;
 #pragma unroll
@@ -439,7 +505,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                 }
                 double s0 = 0.0, s1 = 0.0;                   // the evaluator's own s = (x*x + y*y) + z*z (float32 values in float32 mode)
                 if (mixed) {
-                    const double yyj = lds_f64<0>(ya);
+                    if (IWB_T_SKIP) yyj = lds_f64<0>(ya);
                     if (DT == IWB_F64) {
                         const double sxy = xxi + yyj;
                         s0 = sxy + zz0; s1 = sxy + zz1;
@@ -451,7 +517,9 @@ k_energy3d(const __grid_constant__ K3Params P)
 #pragma unroll
                 for (int sh = 0; sh < NSH; ++sh) {
                     if (row_in[sh]) {
+#if IWB_T_IN
                         sh_sum[sh] += t; sh_abs[sh] += ta; sh_cnt[sh] += npl;
+#endif
                     } else {
                         // the reference's own mask multiply (float32 thresholds are float32 values: the compare is exact in double)
                         const bool in0 = (s0 <= P.shell_thr[sh]), in1 = (s1 <= P.shell_thr[sh]);
@@ -466,57 +534,6 @@ k_energy3d(const __grid_constant__ K3Params P)
                 }
             }
         };
-#else
-        auto tally2 = [&](const double (&e)[2], unsigned ya, double xxi) {
-            const double yyj = lds_f64<0>(ya);
-            const double em0 = __hiloint2double(__double2hiint(e[0]) & om0, __double2loint(e[0]) & om0);
-            const double em1 = __hiloint2double(__double2hiint(e[1]) & om1, __double2loint(e[1]) & om1);
-            acc_sum += em0; acc_abs += fabs(em0);
-            acc_sum += em1; acc_abs += fabs(em1);
-            if (em0 < 0.0) cnt3 += 1;
-            if (em1 < 0.0) cnt3 += 1;
-            if (em0 > 0.0) cnt3 += 0x100;
-            if (em1 > 0.0) cnt3 += 0x100;
-            if (((__double2hiint(em0) & 0x7fffffff) | __double2loint(em0)) == 0) cnt3 += 0x10000;
-            if (((__double2hiint(em1) & 0x7fffffff) | __double2loint(em1)) == 0) cnt3 += 0x10000;
-            if (NSH > 0) {
-                // Row test first: s = RN(sxy + zz) is monotone in zz, so if even the tile's smallest zz lies outside
-                // the largest shell, no column of this row is inside any shell (all lanes agree: uniform branch).
-                if (DT == IWB_F64) {
-                    const double sxy = xxi + yyj;
-                    if (sxy + zzmin_s > P.shell_thr_max) return;
-                    const double s0 = sxy + zz0, s1 = sxy + zz1;
-#pragma unroll
-                    for (int sh = 0; sh < NSH; ++sh) {
-                        const bool in0 = (s0 <= P.shell_thr[sh]), in1 = (s1 <= P.shell_thr[sh]);
-                        const double m0 = in0 ? 1.0 : 0.0, m1 = in1 ? 1.0 : 0.0;
-                        sh_sum[sh] = fma(em0, m0, sh_sum[sh]);
-                        sh_abs[sh] = fma(fabs(em0), m0, sh_abs[sh]);
-                        sh_sum[sh] = fma(em1, m1, sh_sum[sh]);
-                        sh_abs[sh] = fma(fabs(em1), m1, sh_abs[sh]);
-                        if (in0 && om0) ++sh_cnt[sh];
-                        if (in1 && om1) ++sh_cnt[sh];
-                    }
-                } else {
-                    const float sxy = __fadd_rn((float)xxi, (float)yyj);
-                    if (__fadd_rn(sxy, (float)zzmin_s) > (float)P.shell_thr_max) return;
-                    const float s0 = __fadd_rn(sxy, (float)zz0), s1 = __fadd_rn(sxy, (float)zz1);
-#pragma unroll
-                    for (int sh = 0; sh < NSH; ++sh) {
-                        const bool in0 = (s0 <= (float)P.shell_thr[sh]), in1 = (s1 <= (float)P.shell_thr[sh]);
-                        const double m0 = in0 ? 1.0 : 0.0, m1 = in1 ? 1.0 : 0.0;
-                        sh_sum[sh] = fma(em0, m0, sh_sum[sh]);
-                        sh_abs[sh] = fma(fabs(em0), m0, sh_abs[sh]);
-                        sh_sum[sh] = fma(em1, m1, sh_sum[sh]);
-                        sh_abs[sh] = fma(fabs(em1), m1, sh_abs[sh]);
-                        if (in0 && om0) ++sh_cnt[sh];
-                        if (in1 && om1) ++sh_cnt[sh];
-                    }
-                }
-            }
-        };
-
-#endif
 
         // ---- one-sided value at a global face: ((a f0) + (b f1)) + (c f2) over three consecutive entries --------
         // `addr` is the entry AT the face, STEP the byte distance to its neighbour along the axis; `hi` selects the
@@ -685,7 +702,8 @@ k_energy3d(const __grid_constant__ K3Params P)
                     const float sA = __fadd_rn((float)xxp, (float)yyA), sB = __fadd_rn((float)xxp, (float)yyB);
                     const float s[4] = {__fadd_rn(sA, (float)zz0), __fadd_rn(sA, (float)zz1),
                                         __fadd_rn(sB, (float)zz0), __fadd_rn(sB, (float)zz1)};
-                    phi_exact_f32ref<4, true>(s, (float)xp, pc, f, origin || !pc.prechecked);
+                    if (DT == IWB_F32_STRICT) phi_f32strict<4>(s, (float)xp, pc, f);
+                    else phi_exact_f32ref<4, true>(s, (float)xp, pc, f, origin || !pc.prechecked);
                 }
                 const unsigned Ap = A + o_p;
                 sts_f64<0>(Ap, f[0]); sts_f64<256>(Ap, f[1]); sts_f64<ROWB>(Ap, f[2]); sts_f64<ROWB + 256>(Ap, f[3]);
@@ -719,7 +737,8 @@ k_energy3d(const __grid_constant__ K3Params P)
                     const float sxy = __fadd_rn((float)xxp, (float)yyj);
                     const float s[2] = {__fadd_rn(sxy, (float)zz0), __fadd_rn(sxy, (float)zz1)};
                     const bool origin_row = (p == P.i_zero) && (j0 - hj + jr == P.j_zero);
-                    phi_exact_f32ref<2, true>(s, (float)xp, pc, f, origin_row || !pc.prechecked);
+                    if (DT == IWB_F32_STRICT) phi_f32strict<2>(s, (float)xp, pc, f);
+                    else phi_exact_f32ref<2, true>(s, (float)xp, pc, f, origin_row || !pc.prechecked);
                 }
                 const unsigned Ap = A + o_p;
                 sts_f64<0>(Ap, f[0]);
@@ -788,7 +807,7 @@ k_energy3d(const __grid_constant__ K3Params P)
             unsigned cw[NCW];
             {
                 int c[2 * NCW];
-#if IWB_TALLY == 2
+#if IWB_T_INT
                 // neg | NaN | zero were counted; every other output point of this thread in the interval is positive
                 int rows_out = 0;
 #pragma unroll
@@ -861,7 +880,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                         if (is_int) acc = __longlong_as_double(__double_as_longlong(acc) + __double_as_longlong(o));
                         else acc += o;
                     }
-#if IWB_TALLY != 2
+#if !IWB_T_INT
                     // the zero field counted the masked (non-output) columns of every row as well
                     if (q == 4)
                         acc = __longlong_as_double(__double_as_longlong(acc) -
@@ -1024,6 +1043,85 @@ static __global__ void __launch_bounds__(1024) k_combine_chains(const double* __
     s_part[c][q] = (q < ROW) ? gathered[(((size_t)(c % stride) * nfb + fb) * nlc + c / stride) * ROW + q] : 0.0;
     chain_tree(s_part, q, c, nch, is_int);
     if (c == 0 && q < ROW) table[(size_t)fb * ROW + q] = s_part[0][q];
+}
+
+// ---- tile-shard path with the exchange fused in: NVLink peer stores instead of an NCCL all-gather ------------------------
+// k_chain_sums_push is k_chain_sums writing every chain sum straight into the gathered buffer of EVERY rank (its own
+// included) through peer-mapped pointers; k_exchange_combine then signals the peers (one release-store of the epoch per
+// peer, ordered after the push kernel by the stream), waits for the epoch flag of every peer, and runs the chain tree and
+// the row sum of the single-GPU path (the same additions in the same order: bit-identical energies on every rank).
+// Buffers and flags are double-buffered by epoch parity, so a fast rank may already push evaluation e + 1 while a slow one
+// still combines evaluation e; it cannot reach e + 2 before the slow rank has signalled e + 1, i.e. finished reading e.
+constexpr int PEER_MAX = IWB_TILE_CHAINS;
+struct PeerPtrs {
+    double* gath[PEER_MAX];                  // this epoch's gathered buffer [S][nfb][NCH / S][ROW] of every rank (peer-mapped)
+    unsigned long long* flag[PEER_MAX];      // this epoch's flag row [S] of every rank
+};
+
+static __global__ void __launch_bounds__(1024) k_chain_sums_push(const double* __restrict__ partial, const PeerPtrs peers,
+                                                                 int fb_begin, int nfb, int ntiles, int first, int stride,
+                                                                 int nch, unsigned int* counter)
+{
+    if (counter && blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;
+    const int fb = fb_begin + blockIdx.x;
+    const int q = threadIdx.x & 31, lc = threadIdx.x >> 5, nlc = blockDim.x >> 5;
+    if (q >= ROW) return;
+    const double v = chain_sum(partial + (size_t)fb * ntiles * ROW + q, ntiles, first + lc * stride, nch, row_slot_is_int(q));
+    const size_t o = (((size_t)first * nfb + fb) * nlc + lc) * ROW + q;
+    for (int r = 0; r < stride; ++r) peers.gath[r][o] = v;
+}
+
+struct ExchParams {
+    PeerPtrs peers;
+    const double* gath_local;                // this rank's gathered buffer of the epoch
+    const unsigned long long* flag_local;    // this rank's flag row of the epoch
+    unsigned long long epoch;
+    int rank, stride, nfb;
+    double* table;                           // [nfb][ROW] scratch
+    double* row;                             // [ROW] result
+    unsigned int* ticket;                    // 0 at launch; the last block resets it
+};
+
+static __global__ void __launch_bounds__(1024) k_exchange_combine(const ExchParams X)
+{
+    __shared__ double s_part[32][33];
+    __shared__ unsigned s_last;
+    const int fb = blockIdx.x;
+    const int q = threadIdx.x & 31, c = threadIdx.x >> 5, nch = blockDim.x >> 5;
+    // every chain sum of this rank is in place on every peer (the push kernel precedes this one on the stream): tell them
+    if (blockIdx.x == 0 && threadIdx.x < X.stride)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(X.peers.flag[threadIdx.x] + X.rank), "l"(X.epoch) : "memory");
+    if (threadIdx.x < X.stride) {
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(X.flag_local + threadIdx.x) : "memory");
+        } while (seen < X.epoch);
+    }
+    __syncthreads();
+    const int nlc = nch / X.stride;
+    const bool is_int = row_slot_is_int(q);
+    s_part[c][q] = (q < ROW) ? __ldcg(X.gath_local + (((size_t)(c % X.stride) * X.nfb + fb) * nlc + c / X.stride) * ROW + q) : 0.0;
+    chain_tree(s_part, q, c, nch, is_int);
+    if (c == 0 && q < ROW) X.table[(size_t)fb * ROW + q] = s_part[0][q];
+    // the last block to finish adds the rows in index order (k_reduce_rows)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(X.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < ROW) {
+        const int qq = threadIdx.x;
+        const bool ii = row_slot_is_int(qq);
+        double a = 0.0;
+        long long ia = 0;
+        for (int r = 0; r < X.nfb; ++r) {
+            const double v = __ldcg(X.table + (size_t)r * ROW + qq);
+            if (ii) ia += __double_as_longlong(v); else a += v;
+        }
+        X.row[qq] = ii ? __longlong_as_double(ia) : a;
+    }
+    if (threadIdx.x == 0) *X.ticket = 0u;
 }
 
 // ---- fixed-order sum over flush blocks: table[nrows][ROW] -> out[ROW] ------------------------------

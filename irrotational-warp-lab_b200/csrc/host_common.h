@@ -84,6 +84,18 @@ inline void apply_reference_nonfinite(iwb_result* r, int nshell)
     }
 }
 
+// Staging of one non-blocking launch (iwb_energy3d_slab_async / _tiles_async / _tiles_exchange_async): the pinned
+// coordinate buffer, its device copy, the per-tile partial rows and the work counter.  The handle keeps a small ring of
+// them; a slot is reused only after the event recorded behind its previous launch has completed, so calls on different
+// streams never share staging memory and no call has to synchronise its stream.
+struct AsyncSlot {
+    PinBuf h_coords;
+    DevBuf coords, partial, counter;
+    cudaEvent_t done = nullptr;
+    bool in_flight = false;
+};
+constexpr int NASYNC = 4;
+
 constexpr int NSCRATCH = 4;
 constexpr size_t ROW_BYTES_MIN = IWB_ROW_WIDTH * sizeof(double);
 
@@ -94,6 +106,8 @@ struct iwb_handle {
     int sm_count = 0;
     cudaDeviceProp prop;
     iwb::Scratch scr[iwb::NSCRATCH];
+    iwb::AsyncSlot aslot[iwb::NASYNC];
+    int next_aslot = 0;
     int k3_config = 0;         // kernel geometry variant (IWB_K3_CONFIG env override)
     int k3_static_pct = -1;    // share of the work units handed out as one large span per CTA; -1 = automatic (80 / 70 %),
                                // IWB_K3_STATIC_PCT env override

@@ -21,8 +21,49 @@ from .backend import BACKEND_NAME, EPS, _ShellClosure, _grid, summary_metrics
 from .engine import get_engine
 
 
+_PEER_GROUPS: dict = {}      # (process group, device) -> PeerGroup, or None when the peer exchange is unavailable
+PEER_NFB_DEFAULT = 256       # flush blocks the peer buffers are sized for (n <= 4096); grown on demand
+
+
+def peer_group_for(eng, group, nfb: int):
+    """The peer-memory exchange group of ``group`` on this rank's device (created collectively on first use), or None
+    when CUDA IPC / peer access is not available between the ranks -- then the NCCL all-gather is used instead."""
+    import torch
+    import torch.distributed as dist
+
+    key = (group, eng.device)
+    have = _PEER_GROUPS.get(key, False)
+    if have is None or (have is not False and have.nfb_max >= nfb):
+        return have
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if have is not False:
+        have.close()
+
+    def exchange(blob):
+        box = [None] * world
+        dist.all_gather_object(box, blob, group=group)
+        return box
+
+    try:
+        pg = eng.peer_group(rank, world, max(nfb, PEER_NFB_DEFAULT), exchange)
+    except (RuntimeError, ValueError):
+        pg = None
+    # all or nothing: a rank that could not map its peers takes everybody back to NCCL
+    ok = torch.tensor([1 if pg is not None else 0], dtype=torch.int32, device=torch.device("cuda", eng.device))
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 0:
+        if pg is not None:
+            pg.close()
+        pg = None
+    _PEER_GROUPS[key] = pg
+    return pg
+
+
 def compute_energy_3d_sharded(*, rho, sigma, v, extent, n, dtype="float64", shells=None, group=None,
-                              device=None, shard="auto") -> dict:
+                              device=None, shard="auto", exchange="auto") -> dict:
+    """``exchange``: how the chain sums of the tile-shard mode travel -- ``"peer"`` (NVLink peer stores fused behind the
+    kernel, ``iwb_energy3d_tiles_exchange_async``), ``"nccl"`` (``all_gather_into_tensor``), or ``"auto"`` (peer when the
+    ranks can map each other's memory, else NCCL).  Both give the same bits."""
     import torch
     import torch.distributed as dist
 
@@ -36,10 +77,27 @@ def compute_energy_3d_sharded(*, rho, sigma, v, extent, n, dtype="float64", shel
     tiles = None if shard == "slab" else sharding.tile_shard(world, rank)
     if shard == "tiles" and tiles is None:
         raise ValueError(f"shard='tiles' needs a world size that divides {TILE_CHAINS}, got {world}")
+    if exchange not in ("auto", "peer", "nccl"):
+        raise ValueError(f"Unknown exchange: {exchange!r} (expected: auto|peer|nccl)")
+    peers = None
+    if tiles is not None and world > 1 and exchange != "nccl":
+        peers = peer_group_for(eng, group, sharding.num_flush_blocks(n))
+        if peers is None and exchange == "peer":
+            raise RuntimeError("exchange='peer' requested but the ranks cannot map each other's device memory")
 
     def evaluate_tiles(radii):
         nfb = sharding.num_flush_blocks(n)
         stride, first = tiles
+        if peers is not None:
+            row = torch.empty(ROW_WIDTH, dtype=torch.float64, device=dev)
+            stream = torch.cuda.current_stream(dev)
+            keep = peers.energy3d_tiles_exchange_async(row.data_ptr(), stream.cuda_stream, x=x, y=x, z=x, dx=dx, dy=dx, dz=dx,
+                                                       rho=rho, sigma=sigma, v=v, dtype=dtype, shells=radii, eps=EPS)
+            res = eng.read_row(row.data_ptr(), len(radii), stream.cuda_stream)
+            res["cnt_nan"] = n ** 3 - res["cnt_pos"] - res["cnt_neg"] - res["cnt_zero"]
+            sharding.apply_reference_nonfinite(res)
+            del keep
+            return res
         local = torch.empty((nfb, TILE_CHAINS // stride, ROW_WIDTH), dtype=torch.float64, device=dev)   # fully written
         stream = torch.cuda.current_stream(dev)
         keep = eng.energy3d_tiles_async(local.data_ptr(), stream.cuda_stream, x=x, y=x, z=x, dx=dx, dy=dx, dz=dx,
@@ -86,6 +144,7 @@ def compute_energy_3d_sharded(*, rho, sigma, v, extent, n, dtype="float64", shel
                    "shell_points": dict(zip(shells, res["shell_cnt"]))},
         "engine": {"name": "irrotational-warp-lab_b200", "device": eng.name, "world_size": world,
                    "shard": "tiles" if tiles is not None else "slab",
+                   "exchange": ("peer" if peers is not None else "nccl") if world > 1 else "none",
                    "slab": [0, n] if tiles is not None else list(sharding.slab_bounds(n, world)[rank])},
         "_e_at_r": _ShellClosure(lambda radii, out=None: evaluate(radii), known),
     }

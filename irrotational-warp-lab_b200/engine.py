@@ -59,7 +59,11 @@ class Engine:
         if len(shells) > _capi.MAX_SHELLS:
             raise ValueError(f"at most {_capi.MAX_SHELLS} shell radii per call")
         p = _capi.Params3D()
-        p.dtype = _capi.F32_REF if dtype == "float32" else _capi.F64
+        if dtype not in ("float64", "float32", "float32_strict"):
+            raise ValueError(f"Unknown dtype: {dtype!r} (expected: float64|float32|float32_strict)")
+        # "float32" is the reference's --dtype float32 as NumPy >= 2 evaluates it (mixed precision, bit for bit);
+        # "float32_strict" evaluates phi entirely in float32 on the FP32 pipe (no reference semantics, tolerance only)
+        p.dtype = {"float64": _capi.F64, "float32": _capi.F32_REF, "float32_strict": _capi.F32_STRICT}[dtype]
         if mode not in ("exact", "fast"):
             raise ValueError(f"Unknown mode: {mode!r} (expected: exact|fast)")
         p.mode = _capi.MODE_FAST if mode == "fast" else _capi.MODE_EXACT
@@ -171,6 +175,17 @@ class Engine:
                                                       C.c_void_p(int(stream_ptr or 0)), C.c_void_p(int(scratch_ptr)),
                                                       C.c_void_p(int(row_ptr))))
 
+    def read_row(self, row_ptr, nshell, stream_ptr=None):
+        """Blocking copy of a device result row (ROW_WIDTH doubles) to the host, unpacked (iwb_read_row)."""
+        r = _capi.Result()
+        _capi.check(self._lib.iwb_read_row(self._h, C.c_void_p(int(row_ptr)), int(nshell), C.c_void_p(int(stream_ptr or 0)),
+                                           C.byref(r)))
+        return self._result_dict(r, nshell)
+
+    def peer_group(self, rank, world, nfb_max, exchange_handles):
+        """Peer-memory exchange group of ``world`` single-GPU processes on one node (see :class:`PeerGroup`)."""
+        return PeerGroup(self, rank, world, nfb_max, exchange_handles)
+
     def plan3d(self, **kw):
         """Prepared evaluation (coordinates resident on the device); see :class:`Plan3D`."""
         return Plan3D(self, **kw)
@@ -187,6 +202,8 @@ class Engine:
         shells = [float(s) for s in shells]
         if len(shells) > _capi.MAX_SHELLS:
             raise ValueError(f"at most {_capi.MAX_SHELLS} shell radii per call")
+        if dtype not in ("float64", "float32"):
+            raise ValueError(f"Unknown dtype: {dtype!r} (expected: float64|float32; float32_strict exists for the 3D evaluator only)")
         p = _capi.ParamsAxisym()
         p.dtype = _capi.F32_REF if dtype == "float32" else _capi.F64
         p.mode = _capi.MODE_EXACT
@@ -264,9 +281,60 @@ class Plan3D:
     def run_async(self, table_ptr, stream_ptr=None):
         _capi.check(self._eng._lib.iwb_plan3d_run_async(self._h, C.c_void_p(int(table_ptr)), C.c_void_p(int(stream_ptr or 0))))
 
+    def run_exchange_async(self, peers: "PeerGroup", row_ptr, stream_ptr=None):
+        """Collective: this rank's prepared tile shard with the fused peer exchange; result row in ``row_ptr``."""
+        _capi.check(self._eng._lib.iwb_plan3d_run_exchange_async(self._h, peers._h, C.c_void_p(int(stream_ptr or 0)),
+                                                                  C.c_void_p(int(row_ptr))))
+
     def close(self):
         if self._h:
             self._eng._lib.iwb_plan3d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PeerGroup:
+    """``iwb_peer``: the buffers through which the ranks of a tile-sharded evaluation exchange their chain sums as NVLink
+    peer stores (no NCCL launch).  ``exchange_handles(blob) -> list[bytes]`` is the host collective that returns every
+    rank's 64-byte IPC handle in rank order (e.g. ``torch.distributed.all_gather_object``); creation is collective."""
+
+    def __init__(self, eng: Engine, rank: int, world: int, nfb_max: int, exchange_handles):
+        self._eng = eng
+        self.rank, self.world, self.nfb_max = int(rank), int(world), int(nfb_max)
+        h = C.c_void_p()
+        blob = C.create_string_buffer(_capi.PEER_HANDLE_BYTES)
+        _capi.check(eng._lib.iwb_peer_create(eng._h, self.rank, self.world, self.nfb_max, C.byref(h), blob))
+        self._h = h
+        if exchange_handles is None:          # emulated ranks of one process: connect_local() follows (tests)
+            return
+        handles = exchange_handles(bytes(blob.raw))
+        if len(handles) != self.world or any(len(b) != _capi.PEER_HANDLE_BYTES for b in handles):
+            raise RuntimeError("peer exchange: the handle collective returned a malformed list")
+        joined = C.create_string_buffer(b"".join(handles), self.world * _capi.PEER_HANDLE_BYTES)
+        _capi.check(eng._lib.iwb_peer_connect(self._h, joined))
+
+    @staticmethod
+    def connect_local(groups):
+        """Test hook: connect the emulated ranks ``groups`` (all created in this process with ``exchange_handles=None``)."""
+        arr = (C.c_void_p * len(groups))(*[g._h for g in groups])
+        for g in groups:
+            _capi.check(g._eng._lib.iwb_debug_peer_connect_local(g._h, arr))
+
+    def energy3d_tiles_exchange_async(self, row_ptr, stream_ptr=None, **kw):
+        """Collective: kernel + peer push of the chain sums + combine; the result row lands in ``row_ptr`` (device)."""
+        p, keep = Engine.make_params3d(tile_stride=self.world, tile_first=self.rank, **kw)
+        _capi.check(self._eng._lib.iwb_energy3d_tiles_exchange_async(self._eng._h, self._h, C.byref(p),
+                                                                     C.c_void_p(int(stream_ptr or 0)), C.c_void_p(int(row_ptr))))
+        return keep
+
+    def close(self):
+        if self._h:
+            self._eng._lib.iwb_peer_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -77,10 +77,37 @@ def _points_3d(param_list, rho, extent, n, dtype):
                  shells=[], eps=EPS) for s, v in param_list]
 
 
-def evaluate_objective_3d_batch(param_list, rho: float, extent: float, n: int, dtype: str = "float64") -> list:
-    """|E-| of the 3D volume for a list of (sigma, v) points: one ``iwb_energy3d_batch`` call."""
-    res = get_engine().energy3d_batch(_points_3d(param_list, rho, extent, n, dtype))
-    return [abs(r["e_neg"]) for r in res]
+def evaluate_objective_3d_batch(param_list, rho: float, extent: float, n: int, dtype: str = "float64",
+                                distributed: bool = False, group=None) -> list:
+    """|E-| of the 3D volume for a list of (sigma, v) points: one ``iwb_energy3d_batch`` call (several evaluations in
+    flight on the device, one host synchronisation).
+
+    With ``distributed=True`` (or an explicit ``group``) the call is COLLECTIVE over the ``torch.distributed`` group: the
+    points are dealt round-robin to the ranks (point q -> rank q mod P), every rank evaluates its
+    share on its own GPU, and one all-gather of the values gives every rank the full list -- the ``n_initial_points`` /
+    grid batches of BASELINE config 5 spread over the GPUs of a node."""
+    param_list = list(param_list)
+    if not (distributed or group is not None):
+        res = get_engine().energy3d_batch(_points_3d(param_list, rho, extent, n, dtype))
+        return [abs(r["e_neg"]) for r in res]
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("evaluate_objective_3d_batch(distributed=True) needs an initialised torch.distributed process group")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = list(range(rank, len(param_list), world))
+    res = get_engine().energy3d_batch(_points_3d([param_list[q] for q in mine], rho, extent, n, dtype)) if mine else []
+    width = -(-len(param_list) // world) if param_list else 0
+    use_cuda = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+    local = torch.full((max(width, 1),), float("nan"), dtype=torch.float64)
+    for k, r in enumerate(res):
+        local[k] = abs(r["e_neg"])
+    local = local.to(dev)
+    full = torch.empty((world, max(width, 1)), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(full.view(-1), local, group=group)
+    full = full.cpu()
+    return [float(full[q % world, q // world]) for q in range(len(param_list))]
 
 
 def objective_neg_energy_3d(params, param_names, rho: float, extent: float, n: int, dtype: str = "float64") -> float:

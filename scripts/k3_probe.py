@@ -9,7 +9,7 @@ n = int(sys.argv[1]); reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 dtype = sys.argv[3] if len(sys.argv) > 3 else "float64"
 mode = os.environ.get("IWB_MODE", "exact")
 eng = get_engine()
-x = np.linspace(-66.0, 66.0, n, dtype=np.float32 if dtype == "float32" else np.float64); dx = float(x[1] - x[0])
+x = np.linspace(-66.0, 66.0, n, dtype=np.float32 if dtype.startswith("float32") else np.float64); dx = float(x[1] - x[0])
 ts = []
 for rep in range(reps):
     r = eng.energy3d(x=x, y=x, z=x, dx=dx, dy=dx, dz=dx, rho=5.0, sigma=4.0, v=1.0, dtype=dtype, shells=[40.0, 60.0], mode=mode)
