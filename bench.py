@@ -54,8 +54,8 @@ SLOTS_EXACT_ALG = 92.0
 # per-launch figures of k_energy3d at n = 1024^3 on one GPU from the committed `ncu --set full` capture of this build
 # (profiles/r2_k_energy3d_n1024_summary.txt): executed FP64 thread instructions per point, DRAM bytes read + written
 NCU_CAPTURE = "profiles/r2_k_energy3d_n1024_summary.txt"
-NCU_FP64_EXECUTED_PER_POINT = 103.6
-NCU_DRAM_BYTES_PER_LAUNCH = 111616 + 0
+NCU_FP64_EXECUTED_PER_POINT = 102.6
+NCU_DRAM_BYTES_PER_LAUNCH = 110848 + 0
 CPU_SAMPLE_N = 256
 FP64_LANES_PER_SM = 64
 
@@ -465,6 +465,14 @@ def main(argv=None):
     kern_ms_avg = sum(kern_ms) / max(len(kern_ms), 1)
     launches_kernel_only = 2 * len(kern_ms)
 
+    # The clock sampler covers the device-timed legs only: its 100 ms nvidia-smi polling stalls the driver for a moment at
+    # every tick, which blocking calls (one synchronisation per step) feel directly -- 0.3 ms per 9.4 ms step in round 2's
+    # first runs -- while the queued launches of the legs above do not.
+    clocks = None
+    if rank == 0:
+        sampler.stop()
+        clocks = sampler.summary(t_region0, time.perf_counter())
+
     # ---------------- e2e: public API, host buffers, wall clock ------------------------------------------
     def api_step():
         if world > 1:
@@ -487,9 +495,6 @@ def main(argv=None):
     e2e_value = n ** 3 * steps / e2e_s / 1e9
     launches_e2e = (warmup + steps) * (3 if (world == 1 or peers is not None) else 4)
     gc.enable()
-    if rank == 0:
-        sampler.stop()
-    clocks = sampler.summary(t_region0, time.perf_counter()) if rank == 0 else None
 
     # the two paths agree bit for bit, and with the frozen full-volume answer
     assert run["energies"]["e_pos"] == res["e_pos"] and run["energies"]["e_neg"] == res["e_neg"], "paths disagree"

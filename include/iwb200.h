@@ -59,12 +59,11 @@ enum iwb_status {
 /* arithmetic variants */
 enum iwb_dtype {
     IWB_F64 = 0,       /* reference --dtype float64                                          */
-    IWB_F32_REF = 1,   /* reference --dtype float32 as NumPy>=2 evaluates it: float32 grid,   */
+    IWB_F32_REF = 1    /* reference --dtype float32 as NumPy>=2 evaluates it: float32 grid,   */
                        /* r, log-cosh and cos(theta); float64 from sinh(rho*sigma) onwards    */
-    IWB_F32_STRICT = 2 /* float32 grid and EVERY operation of phi in float32 (FP32 pipe); the stencils run in   */
-                       /* float64 on the float32-valued field.  3D evaluator only.  No reference semantics: within */
-                       /* 1e-5 of the reference's float32 mode up to n ~ 200, outside it on finer grids (the phi    */
-                       /* rounding error is divided by dx^2) -- DESIGN.md section 2 has the measured error per n   */
+                       /* (an all-float32 phi was built and measured in round 2: slower -- IEEE float32 division */
+                       /* and square root plus conversions -- and 8e-4 from this mode at n = 1024, so it was     */
+                       /* removed; DESIGN.md section 2, profiles/r2_f32_error_table.log)                         */
 };
 
 enum iwb_mode {

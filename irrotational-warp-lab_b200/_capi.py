@@ -19,7 +19,7 @@ ROW_WIDTH = 6 + 3 * MAX_SHELLS
 PEER_HANDLE_BYTES = 64
 
 OK, ERR_INVALID, ERR_GRID_TOO_SMALL, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM = range(6)
-F64, F32_REF, F32_STRICT = 0, 1, 2
+F64, F32_REF = 0, 1
 MODE_EXACT, MODE_FAST = 0, 1
 
 _dp = C.POINTER(C.c_double)

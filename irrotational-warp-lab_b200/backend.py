@@ -56,7 +56,7 @@ def two_point_tail_extrapolation(e_r1: float, e_r2: float, r1: float, r2: float)
 
 
 def _np_dtype(dtype: str):
-    return np.float32 if dtype in ("float32", "float32_strict") else np.float64
+    return np.float32 if dtype == "float32" else np.float64
 
 
 def _grid(lo, hi, n, dtype):

@@ -34,7 +34,6 @@ UNITS = {
     "core.cu": [],
     "energy3d.cu": ["-fmad=false"] + ([f"-DIWB_DBG={os.environ['IWB_DBG']}"] if os.environ.get("IWB_DBG") else []) + ([f"-DIWB_BARRIER_BACKOFF_NS={os.environ['IWB_BACKOFF']}"] if os.environ.get("IWB_BACKOFF") else []),
     "energy3d_fast.cu": ["-fmad=true"],
-    "energy3d_f32.cu": ["-fmad=false"],
     "planar.cu": ["-fmad=false"],
     "einstein.cu": ["-fmad=false"],
 }

@@ -19,7 +19,6 @@ namespace iwb {
 static cudaError_t launch_k3(int dtype, int mode, int nshell, bool emit, int cfg, const K3Params& P, int sm_count, cudaStream_t st)
 {
     if (mode == IWB_MODE_FAST) return launch_k3_fast(nshell, emit, cfg, P, sm_count, st);
-    if (dtype == IWB_F32_STRICT) return launch_k3_f32strict(nshell, emit, cfg, P, sm_count, st);
     if (dtype == IWB_F64)
         return emit ? launch_nsh<IWB_F64, true, 0>(nshell, cfg, P, sm_count, st)
                     : launch_nsh<IWB_F64, false, 0>(nshell, cfg, P, sm_count, st);
@@ -30,10 +29,8 @@ static cudaError_t launch_k3(int dtype, int mode, int nshell, bool emit, int cfg
 static int validate(const iwb_params3d* p)
 {
     if (!p) return fail(IWB_ERR_INVALID, "params is NULL");
-    if (p->dtype != IWB_F64 && p->dtype != IWB_F32_REF && p->dtype != IWB_F32_STRICT)
-        return fail(IWB_ERR_INVALID, "energy3d: dtype must be IWB_F64, IWB_F32_REF or IWB_F32_STRICT");
-    if (p->dtype == IWB_F32_STRICT && !(isfinite((float)p->sinh_rs) && isfinite((float)p->cosh_rs)))
-        return fail(IWB_ERR_INVALID, "energy3d: IWB_F32_STRICT needs sinh(rho*sigma) finite in float32 (rho*sigma < 88)");
+    if (p->dtype != IWB_F64 && p->dtype != IWB_F32_REF)
+        return fail(IWB_ERR_INVALID, "energy3d: dtype must be IWB_F64 or IWB_F32_REF");
     if (p->mode != IWB_MODE_EXACT && p->mode != IWB_MODE_FAST) return fail(IWB_ERR_INVALID, "energy3d: unknown mode");
     if (p->mode == IWB_MODE_FAST && p->dtype != IWB_F64)
         return fail(IWB_ERR_INVALID, "energy3d: IWB_MODE_FAST exists for IWB_F64 only");
@@ -470,7 +467,7 @@ int iwb_debug_tiles_j(int n, int* out, int cap)
     const int rj = kConfigs[1].rj;       // the default geometry (region of 40 rows)
     const int nt = tiles_j(n, rj);
     for (int t = 0; t <= nt && t < cap; ++t)
-        if (out) out[t] = tile_begin_j(t, nt, n, rj);
+        if (out) out[t] = tile_begin_j(t, nt, n);
     return nt;
 }
 

@@ -45,49 +45,12 @@
 #ifndef IWB_BARRIER_BACKOFF_NS
 #define IWB_BARRIER_BACKOFF_NS 100
 #endif
-#ifndef IWB_FLUSH_PACK
-#define IWB_FLUSH_PACK 1    // counts packed two per 32-bit word in the flush butterfly (+0.5 %)
-#endif
 
-#ifndef IWB_SUM_RHO
-#define IWB_SUM_RHO 0       // 1: tally rho and multiply by dV at the flush: one DMUL per point less, +0.8 % on B200
-                            // (profiles/r2_ab3_tally_nbsync.log).  NOT adopted: the reference classifies e = rho * dV, and a
-                            // rho whose product with dV underflows would be counted with its sign instead of as a zero
-#endif
 #ifndef IWB_OC_UNROLL
 #define IWB_OC_UNROLL 1     // both rows of the O + C loop unrolled: no loop overhead, row b's loads overlap row a's tally (+0.9 %)
 #endif
 #ifndef IWB_P4
 #define IWB_P4 1       // task P evaluates both rows of a warp at once: four independent phi evaluations per thread
-#endif
-#ifndef IWB_JFACE
-#define IWB_JFACE 0    // 1: tiles at the two j faces hold RJ - 2 output rows (no halo beyond the face), as the k-face tiles hold
-                       // RK - 2 columns: n = 256 is 7 instead of 8 tile rows, n = 400 11 instead of 12.  Measured on B200
-                       // (profiles/r2_ab2_tally_jface.log): n = 256 / 400 +2 %, n = 1024 -4 % (the row offset costs the hot
-                       // loops registers), so it is off; round 1 saw the same with its own version.
-#endif
-#ifndef IWB_TALLY
-#define IWB_TALLY 3    // 1: round-1 tally (two FP64 compares per point, per-row shell test from (x*x + y*y) + zz_min)
-                       // 3: + "row outside every shell" from a per-tile table of x*x limits (two additions per row less)
-                       // 4: integer sign count with an exact rare path for zero / NaN / inf instead of the FP64 compares
-                       // 2: 3 + 4 + "row fully inside shell s" tables with pair sums
-                       // B200, n = 1024^3 (profiles/r2_ab2_tally_jface.log, r2_ab3_tally_nbsync.log): 1: 114.2, 3: 115.5,
-                       // 4: 113.0, 2: 113.4 Gpoints/s -- the variants that issue fewer instructions are not the faster ones
-#endif
-#define IWB_T_INT (IWB_TALLY == 2 || IWB_TALLY == 4)    // integer sign count + exact rare path (zero / NaN / inf), positives derived
-#define IWB_T_SKIP (IWB_TALLY == 2 || IWB_TALLY == 3)   // "row outside every shell" from a per-tile table instead of two additions per row
-#define IWB_T_IN (IWB_TALLY == 2)                        // "row fully inside shell s" tables + pair sums
-#if !IWB_FLUSH_PACK && IWB_T_INT
-#error "IWB_TALLY == 2 derives the positive count in the packed flush only"
-#endif
-#ifndef IWB_NBSYNC
-#define IWB_NBSYNC 0   // neighbour-only synchronisation of the march instead of one CTA-wide mbarrier phase per plane:
-                       // 1 / 2: progress counters in shared memory (release / volatile stores); 3: two mbarriers per warp.
-                       // Measured on B200 at n = 1024^3: 0: 113.3 / 114.2, 1: 108.8, 2: 109.0, 3: 111.8 Gpoints/s -- the
-                       // CTA-wide split barrier is the fastest (profiles/r2_ab1_*.log, r2_ab3_*.log); kept for the record
-#endif
-#ifndef IWB_DBG
-#define IWB_DBG 0      // development only: 1 = skip task O, 2 = skip the phi evaluation, 3 = both
 #endif
 
 namespace iwb {
@@ -96,9 +59,7 @@ constexpr int RK = 64;              // region columns (k): two per lane
 constexpr int TK_MAX = RK - 4;      // tile columns
 constexpr int ROW = IWB_ROW_WIDTH;  // doubles per partial row
 constexpr int FLUSH = IWB_FLUSH_PLANES;
-constexpr int SMEM_PAD = 8;         // guard doubles after the planes (lane 31 reads idx + 1)
-constexpr int SMEM_PAD_FRONT = IWB_JFACE ? RK + 8 : 8;   // guard before the planes: lane 0 reads idx - 1, and the central formula
-                                    // of a face row reads the row below region row 0 before the one-sided formula overrides it
+constexpr int SMEM_PAD = 8;         // guard doubles before and after the planes (lane 0 / lane 31 reads of idx -+ 1)
 constexpr int NPLANES = 11;
 constexpr int NEDGE = 18;           // one-sided coefficients a0 b0 c0 a1 b1 c1 of the three axes (shared-memory copy)
 
@@ -147,24 +108,11 @@ __host__ __device__ inline int tile_begin_1d(int t, int nt, int n, int R)
 }
 __host__ __device__ inline int tiles_k(int n) { return tiles_1d(n, RK); }
 __host__ __device__ inline int tile_begin_k(int t, int nt, int n) { return tile_begin_1d(t, nt, n, RK); }
-// rows (j) of a region of RJ rows
-__host__ __device__ inline int tiles_j(int n, int RJ)
-{
-#if IWB_JFACE
-    return tiles_1d(n, RJ);
-#else
-    return (n + (RJ - 4) - 1) / (RJ - 4);
-#endif
-}
-__host__ __device__ inline int tile_begin_j(int t, int nt, int n, int RJ)
-{
-#if IWB_JFACE
-    return tile_begin_1d(t, nt, n, RJ);
-#else
-    (void)RJ;
-    return tile_begin(t, nt, n);
-#endif
-}
+// Rows (j) of a region of RJ rows: an even split into tiles of at most RJ - 4 output rows.  (Face tiles of RJ - 2 rows,
+// as for the columns, were measured twice: one tile row less at n = 256 / 400 (+2 %), but -4 % at n = 1024, where the
+// tile count does not change and the row offset costs the hot loops registers -- profiles/r2_k_energy3d_history.txt.)
+__host__ __device__ inline int tiles_j(int n, int RJ) { return (n + (RJ - 4) - 1) / (RJ - 4); }
+__host__ __device__ inline int tile_begin_j(int t, int nt, int n) { return tile_begin(t, nt, n); }
 
 template <int RJ, int NW>
 struct Geo {
@@ -172,8 +120,8 @@ struct Geo {
     static constexpr int TJ_MAX = RJ - 4;
     static constexpr int NT = NW * 32;
     static constexpr int SCRATCH = NW * ROW;     // block-reduction scratch (doubles)
-    static constexpr int NROWTAB = IWB_T_IN ? 4 : (IWB_T_SKIP ? 2 : 1);     // per-row tables: y*y [, x*x limits: outside all shells, inside shell 0, 1]
-    static constexpr size_t SMEM_BYTES = (size_t(NPLANES) * PLANE + SMEM_PAD_FRONT + SMEM_PAD + NROWTAB * RJ + SCRATCH + NEDGE) * sizeof(double);
+    static constexpr int NROWTAB = 2;            // per-row tables: y*y, and the largest x*x for which the row can hold a shell point
+    static constexpr size_t SMEM_BYTES = (size_t(NPLANES) * PLANE + 2 * SMEM_PAD + NROWTAB * RJ + SCRATCH + NEDGE) * sizeof(double);
 };
 
 template <int DT, int NSH, int RJ, int NW, bool EMIT, int MINB = 1, int MODE = 0>
@@ -184,11 +132,11 @@ k_energy3d(const __grid_constant__ K3Params P)
     constexpr int PLANE = G::PLANE;
     constexpr int NSHA = NSH > 0 ? NSH : 1;
     extern __shared__ double smem_raw[];
-    double* const phi_ring = smem_raw + SMEM_PAD_FRONT;    // 3 planes
+    double* const phi_ring = smem_raw + SMEM_PAD;          // 3 planes
     double* const px_ring = phi_ring + 3 * PLANE;          // 4 planes
     double* const py_buf = phi_ring + 7 * PLANE;           // 2 planes
     double* const pz_buf = phi_ring + 9 * PLANE;           // 2 planes
-    double* const yy_s = phi_ring + NPLANES * PLANE + SMEM_PAD;   // [RJ] y*y of the region rows [+ 3 x RJ shell-test limits]
+    double* const yy_s = phi_ring + NPLANES * PLANE + SMEM_PAD;   // [RJ] y*y of the region rows, then [RJ] shell-test limits on x*x
     double* const scratch = yy_s + G::NROWTAB * RJ;        // [NW][ROW]
     // One-sided (global face) coefficients live in shared memory: only the edge flavours of the tasks read them,
     // and as kernel parameters they would occupy 36 uniform registers that the interior loops need for their constants.
@@ -221,82 +169,6 @@ k_energy3d(const __grid_constant__ K3Params P)
         ec_s[threadIdx.x] = (&P.cx.h2)[8 * axis + 2 + q];
     }
     __syncthreads();
-#if IWB_NBSYNC == 3
-    // Neighbour synchronisation with hardware waits: every warp owns TWO mbarriers (even / odd steps, 32 arrivals each);
-    // after O(i) + C(i+1) of step t it arrives on its barrier t & 1, and before step t + 1 it waits for phase t >> 1 of
-    // both row neighbours' barrier t & 1.  A neighbour cannot arrive at step t + 2 (the next phase of the same barrier)
-    // before this warp has arrived at step t + 1, so the parity is unambiguous.  Entry 0 / NW + 1 of each row mirror the
-    // warps NW - 1 / 0 (those two warps arrive twice), which puts the neighbours at -+ 8 bytes of the own entry.
-    __shared__ unsigned long long s_nb[2][NW + 2];
-    static_assert(RJ == 2 * NW, "row neighbours are the warps w -+ 1 only when every warp owns the rows w and w + NW");
-    if (threadIdx.x < 2 * (NW + 2))
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_nb[0][0] + threadIdx.x)), "r"(32));
-    __syncthreads();
-    unsigned nb_step = 0;                                  // march steps completed (same on all lanes)
-    const unsigned nb_me = keep_u32((unsigned)__cvta_generic_to_shared(&s_nb[0][1 + ty]));
-    constexpr int NB_ROW = (NW + 2) * 8;                   // bytes from a warp's even barrier to its odd one
-    auto step_arrive = [&]() {
-        const unsigned a = nb_me + (nb_step & 1u) * NB_ROW;
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
-        if (ty == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+%1];" ::"r"(a), "n"(8 * NW) : "memory");
-        if (ty == NW - 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+%1];" ::"r"(a), "n"(-8 * NW) : "memory");
-    };
-    auto step_wait = [&]() {
-        const unsigned a = nb_me + (nb_step & 1u) * NB_ROW, par = (nb_step >> 1) & 1u;
-        unsigned done;
-        for (;;) {
-            asm volatile("{ .reg .pred p, q; mbarrier.try_wait.parity.shared::cta.b64 p, [%1+-8], %2; "
-                         "mbarrier.try_wait.parity.shared::cta.b64 q, [%1+8], %2; and.pred p, p, q; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(done) : "r"(a), "r"(par) : "memory");
-            if (__all_sync(0xffffffffu, done != 0u)) break;
-            __nanosleep(IWB_BARRIER_BACKOFF_NS);
-        }
-        ++nb_step;
-    };
-#elif IWB_NBSYNC
-    // Neighbour synchronisation of the march.  Every cross-warp dependency of a step runs between ROW neighbours: O(i)
-    // reads phi_x(i), phi_y(i) of the rows j -+ 1, C(i+1) reads phi(i+1) of the rows j -+ 1; columns k -+ 1 belong to the
-    // warp itself, the x direction to the thread itself.  Warp w owns the rows w and w + NW, so its neighbours are the
-    // warps w -+ 1 (cyclically: row NW - 1 belongs to warp NW - 1, row NW to warp 0).  The hazards (read-after-write on
-    // phi_x / phi_y / phi, write-after-read on the phi_y / phi_z buffer and the phi / phi_x ring slots that step i
-    // recycles) all reduce to ONE rule: warp w may start O(i) + C(i+1) once both neighbours have finished
-    // O(i-1) + C(i); task P(i+3) writes own columns only and needs nothing more.  s_prog[w] counts the steps whose
-    // O + C warp w has finished (monotonic over the kernel); neighbours differ by at most one step, distant warps may
-    // drift further, so one slow warp (wall rows, a late wake-up) no longer stops the other nineteen.
-    // s_prog[1 + w] is warp w's counter; entry 0 mirrors warp NW - 1 and entry NW + 1 mirrors warp 0, so that every
-    // warp finds its neighbours at -+ 4 bytes of its own entry (one address register).
-    __shared__ unsigned s_prog[NW + 2];
-    static_assert(RJ == 2 * NW, "row neighbours are the warps w -+ 1 only when every warp owns the rows w and w + NW");
-    if (threadIdx.x < NW + 2) s_prog[threadIdx.x] = 0u;
-    __syncthreads();
-    unsigned nb_step = 0;                                  // march steps completed by this warp (same on all lanes)
-    const unsigned prog_me = keep_u32((unsigned)__cvta_generic_to_shared(&s_prog[1 + ty]));
-    auto step_wait = [&]() {       // before O(i+1) + C(i+2): both neighbours have arrived at this step (and so at every earlier one)
-        for (;;) {
-            unsigned a, b;
-            asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1+-4];" : "=r"(a) : "r"(prog_me) : "memory");
-            asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1+4];" : "=r"(b) : "r"(prog_me) : "memory");
-            // (the vote makes the exit warp-uniform: the code after the loop stays on the uniform datapath)
-            if (__all_sync(0xffffffffu, (int)(a - nb_step) >= 0 && (int)(b - nb_step) >= 0)) break;
-            __nanosleep(IWB_BARRIER_BACKOFF_NS);
-        }
-    };
-    auto step_arrive = [&]() {     // after O(i) + C(i+1)
-        __syncwarp();
-        ++nb_step;
-        if (tx == 0) {
-#if IWB_NBSYNC == 2
-            asm volatile("st.volatile.shared::cta.u32 [%0], %1;" ::"r"(prog_me), "r"(nb_step) : "memory");
-            if (ty == 0) asm volatile("st.volatile.shared::cta.u32 [%0+%2], %1;" ::"r"(prog_me), "r"(nb_step), "n"(4 * NW) : "memory");
-            if (ty == NW - 1) asm volatile("st.volatile.shared::cta.u32 [%0+%2], %1;" ::"r"(prog_me), "r"(nb_step), "n"(-4 * NW) : "memory");
-#else
-            asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(prog_me), "r"(nb_step) : "memory");
-            if (ty == 0) asm volatile("st.relaxed.cta.shared::cta.u32 [%0+%2], %1;" ::"r"(prog_me), "r"(nb_step), "n"(4 * NW) : "memory");
-            if (ty == NW - 1) asm volatile("st.relaxed.cta.shared::cta.u32 [%0+%2], %1;" ::"r"(prog_me), "r"(nb_step), "n"(-4 * NW) : "memory");
-#endif
-        }
-    };
-#else
     auto step_arrive = [&]() { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar_addr) : "memory"); };
     auto step_wait = [&]() {
         unsigned done;
@@ -310,7 +182,6 @@ k_energy3d(const __grid_constant__ K3Params P)
         }
         mbar_parity ^= 1u;
     };
-#endif
     // Work distribution.  A unit is (tile, flush block); units are ordered tile-major, and a SPAN is a contiguous range
     // of units.  A CTA marches through the units of a span without interruption -- the rings stay primed, so only the
     // first unit of a tile within a span pays the 4-plane phi prologue -- and spans are handed out in index order by an
@@ -350,23 +221,21 @@ k_energy3d(const __grid_constant__ K3Params P)
             }
         }
         const int tj = tile / P.ntk, tk = tile - tj * P.ntk;
-        const int j0 = tile_begin_j(tj, P.ntj, P.n1, RJ), Tj = tile_begin_j(tj + 1, P.ntj, P.n1, RJ) - j0;
+        const int j0 = tile_begin_j(tj, P.ntj, P.n1), Tj = tile_begin_j(tj + 1, P.ntj, P.n1) - j0;
         const int k0 = tile_begin_k(tk, P.ntk, P.n2), Tk = tile_begin_k(tk + 1, P.ntk, P.n2) - k0;
         const int hl = (k0 == 0) ? 0 : 2;           // halo columns on the low side: region column c is k = k0 - hl + c
         const int i0 = P.i_begin + fblk0 * FLUSH;
         const int i1 = min(P.i_end, P.i_begin + fblk1 * FLUSH);
 
-        // Region row jr is j = j0 - hj + jr (hj halo rows on the low side); the output rows are [o_lo, o_hi]; the rows
-        // [jr_lo, jr_hi] exist in the grid (j == 0 is region row o_lo of a low-face tile, j == n1-1 row o_hi of a high-face one)
+        // region rows [jr_lo, jr_hi] exist in the grid; j == 0 is region row 2 of a low-edge tile,
+        // j == n1-1 is region row Tj+1 of a high-edge tile
         const bool t_jlo = (j0 == 0), t_jhi = (j0 + Tj == P.n1);
         const bool t_kedge = (k0 == 0) || (k0 + Tk == P.n2);
         const bool tile_edge = t_jlo || t_jhi || t_kedge;
-        const int hj = (IWB_JFACE && t_jlo) ? 0 : 2;
-        const int o_lo = hj, o_hi = hj + Tj - 1;
-        const int jr_lo = t_jlo ? o_lo : 0, jr_hi = t_jhi ? o_hi : o_hi + 2;
-        const int py_lo = max(jr_lo, o_lo - 1), py_hi = min(jr_hi, o_hi + 1);
+        const int jr_lo = t_jlo ? 2 : 0, jr_hi = t_jhi ? Tj + 1 : Tj + 3;
+        const int py_lo = max(jr_lo, 1), py_hi = min(jr_hi, Tj + 2);
 
-        if (threadIdx.x < RJ) yy_s[threadIdx.x] = P.yy[min(max(j0 - hj + (int)threadIdx.x, 0), P.n1 - 1)];
+        if (threadIdx.x < RJ) yy_s[threadIdx.x] = P.yy[min(max(j0 - 2 + (int)threadIdx.x, 0), P.n1 - 1)];
 
         // this lane's two columns
         double zz0, zz1;
@@ -389,34 +258,17 @@ k_energy3d(const __grid_constant__ K3Params P)
             for (int off = 16; off > 0; off >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, off));
             zzmin_s = m;
         }
-        constexpr int NIN = (IWB_T_IN && NSH >= 1 && NSH <= 2) ? NSH : 0;     // shells with a "row fully inside" table
-#if IWB_T_INT || IWB_T_SKIP
-        // hi-word OR-masks that make a non-output column look like 1.0 to the special-value test of the tally, and the
-        // number of output columns of this lane
-        const int fx0 = (int)keep_u32((cf0 & 16u) ? 0u : 0x3ff00000u), fx1 = (int)keep_u32((cf1 & 16u) ? 0u : 0x3ff00000u);
-        const int npl = (int)((cf0 >> 4) & 1u) + (int)((cf1 >> 4) & 1u);
-        if (NSH > 0 && IWB_T_SKIP) {
-            // Row tables of the shell tests.  s = RN(RN(x*x + y*y) + z*z) is monotone in each term, so for a row (fixed y)
-            // of this tile:  x*x > xout[row]  =>  even the column with the smallest z*z lies outside the largest shell;
-            //                x*x <= xin[s][row]  =>  even the column with the largest z*z lies inside shell s.
-            // The limits are conservative (a relative margin far above the rounding errors of s: float64 2^-40, float32
-            // 2^-18), so a row they leave undecided simply takes the exact per-point comparison.
-            double zzmax = fmax((cf0 & 16u) ? zz0 : -INFINITY, (cf1 & 16u) ? zz1 : -INFINITY);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) zzmax = fmax(zzmax, __shfl_xor_sync(0xffffffffu, zzmax, off));
-            if (threadIdx.x < RJ) {
-                const double yyv = P.yy[min(max(j0 - hj + (int)threadIdx.x, 0), P.n1 - 1)];
-                const double mrg = (DT == IWB_F64) ? 0x1p-40 : 0x1p-18;
-                const double tm = P.shell_thr_max;
-                yy_s[RJ + threadIdx.x] = (tm < 0.0) ? -1.0 : ((tm - yyv) - zzmin_s) + ((tm + yyv) + zzmin_s) * mrg;
-#pragma unroll
-                for (int sh = 0; sh < NIN; ++sh) {
-                    const double th = P.shell_thr[sh];
-                    yy_s[(2 + sh) * RJ + threadIdx.x] = (th < 0.0) ? -1.0 : ((th - yyv) - zzmax) - ((th + yyv) + zzmax) * mrg;
-                }
-            }
+        if (NSH > 0 && threadIdx.x < RJ) {
+            // Row table of the shell test.  s = RN(RN(x*x + y*y) + z*z) is monotone in each term, so for a row (fixed y) of
+            // this tile  x*x > xout[row]  means that even the column with the smallest z*z lies outside the largest shell:
+            // the row skips the shell arithmetic after ONE comparison (round 1 formed (x*x + y*y) + zz_min per row).  The
+            // limit is conservative -- a relative margin far above the rounding errors of s (float64 2^-40, float32 2^-18)
+            // -- so a row it leaves undecided simply takes the exact per-point comparisons.
+            const double yyv = P.yy[min(max(j0 - 2 + (int)threadIdx.x, 0), P.n1 - 1)];
+            const double mrg = (DT == IWB_F64) ? 0x1p-40 : 0x1p-18;
+            const double tm = P.shell_thr_max;
+            yy_s[RJ + threadIdx.x] = (tm < 0.0) ? -1.0 : ((tm - yyv) - zzmin_s) + ((tm + yyv) + zzmin_s) * mrg;
         }
-#endif
 
         // ---- accumulators (registers) -------------------------------------------------
         double acc_sum = 0.0, acc_abs = 0.0;        // sum(e), sum(|e|) over the thread's output points
@@ -439,98 +291,43 @@ k_energy3d(const __grid_constant__ K3Params P)
         // Counts: every point is exactly one of neg / pos / zero / NaN; the first three are counted here in 8-bit
         // fields of one register (<= 64 points per thread and flush interval), NaN is derived by the host.  The zero
         // field also counts the masked non-output columns; the flush subtracts their (known) number.
-        // IWB_T_IN: pair sums first (e0 + e1, |e0| + |e1|): the main accumulators and every shell the row lies fully inside
-        // take the same two values.  IWB_T_INT: the sign bit of the masked value counts the negative points; a point whose
-        // high word says zero / tiny / inf / NaN sends its thread through an exact, rare path that counts zeros and NaNs
-        // and takes the sign count back where it does not apply (-0.0, -NaN); positives are derived at the flush
-        // (cnt3 fields: negative | NaN << 8 | zero << 16).
         auto tally2 = [&](const double (&e)[2], unsigned ya, double xxi) {
-            const int h0 = __double2hiint(e[0]), h1 = __double2hiint(e[1]);
-            const int hm0 = h0 & om0, hm1 = h1 & om1;
+            const int hm0 = __double2hiint(e[0]) & om0, hm1 = __double2hiint(e[1]) & om1;
             const double em0 = __hiloint2double(hm0, __double2loint(e[0]) & om0);
             const double em1 = __hiloint2double(hm1, __double2loint(e[1]) & om1);
-            double t = 0.0, ta = 0.0;
-            if (IWB_T_IN) {
-                t = em0 + em1; ta = fabs(em0) + fabs(em1);
-                acc_sum += t; acc_abs += ta;
-            } else {
-                acc_sum += em0; acc_abs += fabs(em0);
-                acc_sum += em1; acc_abs += fabs(em1);
-            }
-#if IWB_T_INT
-            cnt3 += (int)((unsigned)hm0 >> 31) + (int)((unsigned)hm1 >> 31);
-            // |value| < 2^-511 (zero, denormal, or so small that value * dV may underflow when rho is tallied) or exponent
-            // all ones (inf, NaN), at an output column: classify exactly what the reference classifies, e = rho * dV
-            const unsigned u0 = (unsigned)((h0 & 0x7fffffff) | fx0) - 0x20000000u, u1 = (unsigned)((h1 & 0x7fffffff) | fx1) - 0x20000000u;
-            if (max(u0, u1) >= 0x5ff00000u) {
-                const double sc = IWB_SUM_RHO ? P.dV : 1.0;
-                if (om0 && u0 >= 0x5ff00000u) {
-                    const double ev = em0 * sc;
-                    if (ev == 0.0) cnt3 += 0x10000 - (int)((unsigned)hm0 >> 31);
-                    else if (ev != ev) cnt3 += 0x100 - (int)((unsigned)hm0 >> 31);
-                }
-                if (om1 && u1 >= 0x5ff00000u) {
-                    const double ev = em1 * sc;
-                    if (ev == 0.0) cnt3 += 0x10000 - (int)((unsigned)hm1 >> 31);
-                    else if (ev != ev) cnt3 += 0x100 - (int)((unsigned)hm1 >> 31);
-                }
-            }
-#else
-            // every point is exactly one of neg / pos / zero / NaN; the zero field also counts the masked columns
+            acc_sum += em0; acc_abs += fabs(em0);
+            acc_sum += em1; acc_abs += fabs(em1);
             if (em0 < 0.0) cnt3 += 1;
             if (em1 < 0.0) cnt3 += 1;
             if (em0 > 0.0) cnt3 += 0x100;
             if (em1 > 0.0) cnt3 += 0x100;
             if (((hm0 & 0x7fffffff) | __double2loint(em0)) == 0) cnt3 += 0x10000;
             if (((hm1 & 0x7fffffff) | __double2loint(em1)) == 0) cnt3 += 0x10000;
-#endif
             if (NSH > 0) {
-                constexpr int RB = RJ * 8;
-                double yyj = 0.0;
-                if (IWB_T_SKIP) {
-                    if (xxi > lds_f64<RB>(ya)) return;          // no column of this row inside any shell (warp-uniform)
+                // Row test first (warp-uniform): x*x beyond the row's limit means no column of this row lies inside any
+                // shell (table filled above).  Rows that pass compare every point exactly: s is the evaluator's own
+                // (x*x + y*y) + z*z, in float32 arithmetic on the float32 grid.
+                if (xxi > lds_f64<RJ * 8>(ya)) return;
+                const double yyj = lds_f64<0>(ya);
+                double s0, s1;
+                if (DT == IWB_F64) {
+                    const double sxy = xxi + yyj;
+                    s0 = sxy + zz0; s1 = sxy + zz1;
                 } else {
-                    // s = RN(sxy + zz) is monotone in zz: if even the tile's smallest zz lies outside the largest shell, no
-                    // column of this row is inside any shell (all lanes agree: uniform branch)
-                    yyj = lds_f64<0>(ya);
-                    if (DT == IWB_F64) { if ((xxi + yyj) + zzmin_s > P.shell_thr_max) return; }
-                    else if (__fadd_rn(__fadd_rn((float)xxi, (float)yyj), (float)zzmin_s) > (float)P.shell_thr_max) return;
-                }
-                bool row_in[NSHA];
-                bool mixed = false;
-#pragma unroll
-                for (int sh = 0; sh < NSH; ++sh) {
-                    row_in[sh] = (sh < NIN) && (xxi <= (sh == 0 ? lds_f64<2 * RB>(ya) : lds_f64<3 * RB>(ya)));
-                    mixed = mixed || !row_in[sh];
-                }
-                double s0 = 0.0, s1 = 0.0;                   // the evaluator's own s = (x*x + y*y) + z*z (float32 values in float32 mode)
-                if (mixed) {
-                    if (IWB_T_SKIP) yyj = lds_f64<0>(ya);
-                    if (DT == IWB_F64) {
-                        const double sxy = xxi + yyj;
-                        s0 = sxy + zz0; s1 = sxy + zz1;
-                    } else {
-                        const float sxy = __fadd_rn((float)xxi, (float)yyj);
-                        s0 = (double)__fadd_rn(sxy, (float)zz0); s1 = (double)__fadd_rn(sxy, (float)zz1);
-                    }
+                    const float sxy = __fadd_rn((float)xxi, (float)yyj);
+                    s0 = (double)__fadd_rn(sxy, (float)zz0); s1 = (double)__fadd_rn(sxy, (float)zz1);
                 }
 #pragma unroll
                 for (int sh = 0; sh < NSH; ++sh) {
-                    if (row_in[sh]) {
-#if IWB_T_IN
-                        sh_sum[sh] += t; sh_abs[sh] += ta; sh_cnt[sh] += npl;
-#endif
-                    } else {
-                        // the reference's own mask multiply (float32 thresholds are float32 values: the compare is exact in double)
-                        const bool in0 = (s0 <= P.shell_thr[sh]), in1 = (s1 <= P.shell_thr[sh]);
-                        const double m0 = in0 ? 1.0 : 0.0, m1 = in1 ? 1.0 : 0.0;
-                        sh_sum[sh] = fma(em0, m0, sh_sum[sh]);
-                        sh_abs[sh] = fma(fabs(em0), m0, sh_abs[sh]);
-                        sh_sum[sh] = fma(em1, m1, sh_sum[sh]);
-                        sh_abs[sh] = fma(fabs(em1), m1, sh_abs[sh]);
-                        if (in0 && om0) ++sh_cnt[sh];
-                        if (in1 && om1) ++sh_cnt[sh];
-                    }
+                    // the reference's own mask multiply (float32 thresholds are float32 values: the compare is exact in double)
+                    const bool in0 = (s0 <= P.shell_thr[sh]), in1 = (s1 <= P.shell_thr[sh]);
+                    const double m0 = in0 ? 1.0 : 0.0, m1 = in1 ? 1.0 : 0.0;
+                    sh_sum[sh] = fma(em0, m0, sh_sum[sh]);
+                    sh_abs[sh] = fma(fabs(em0), m0, sh_abs[sh]);
+                    sh_sum[sh] = fma(em1, m1, sh_sum[sh]);
+                    sh_abs[sh] = fma(fabs(em1), m1, sh_abs[sh]);
+                    if (in0 && om0) ++sh_cnt[sh];
+                    if (in1 && om1) ++sh_cnt[sh];
                 }
             }
         };
@@ -572,8 +369,8 @@ k_energy3d(const __grid_constant__ K3Params P)
 #pragma unroll 1
 #endif
             for (int jr = ty; jr < RJ; jr += NW, A += ROWB, ya += NW * 8) {
-                const int jedge = (t_jlo && jr == o_lo) ? 1 : ((t_jhi && jr == o_hi) ? 2 : 0);
-                if (doO && jr >= o_lo && jr <= o_hi) {
+                const int jedge = (t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0);
+                if (doO && jr >= 2 && jr <= Tj + 1) {
                     const unsigned Ai = A + o_pxi, Ap = A + o_pxp, Am = A + o_pxm, Ay = A + o_py;
                     // column a = this lane, column b = lane + 32 (256 bytes further)
                     const double xpa = lds_f64<0>(Ap), xma = lds_f64<0>(Am);
@@ -632,21 +429,17 @@ k_energy3d(const __grid_constant__ K3Params P)
                         rho2[a] = cdivm<MODE>(tr * tr - kk, P.c16pi, P.rc16pi);
                     }
                     if (EMIT) {
-                        const long long j = j0 - hj + jr, k = k0 - hl + tx;
+                        const long long j = j0 - 2 + jr, k = k0 - hl + tx;
                         double* dst = P.rho_out + ((long long)(i - P.i_begin) * P.n1 + j) * P.n2 + k;
                         if (cf0 & 16u) dst[0] = rho2[0];
                         if (cf1 & 16u) dst[32] = rho2[1];
                     }
-#if IWB_SUM_RHO
-                    tally2(rho2, ya, xxi);        // sums of rho; the flush multiplies by dV (sign(e) == sign(rho): dV > 0)
-#else
                     const double e2[2] = {rho2[0] * P.dV, rho2[1] * P.dV};
                     tally2(e2, ya, xxi);
-#endif
                 }
                 if (doC && jr >= py_lo && jr <= py_hi) {
                     const unsigned Ah = A + o_ph, Aw = A + o_w;
-                    const bool z_row = (jr >= o_lo && jr <= o_hi);
+                    const bool z_row = (jr >= 2 && jr <= Tj + 1);
                     const double hjpa = lds_f64<R8>(Ah), hjma = lds_f64<-R8>(Ah);
                     const double hjpb = lds_f64<256 + R8>(Ah), hjmb = lds_f64<256 - R8>(Ah);
                     const double hkpa = lds_f64<8>(Ah), hkma = lds_f64<-8>(Ah);
@@ -687,11 +480,11 @@ k_energy3d(const __grid_constant__ K3Params P)
             // Both rows of the warp at once when both exist: the sqrt / division chains of phi are ~20 dependent
             // FP64 operations long, and four independent evaluations per thread (instead of two) keep the FP64 pipe
             // fed with five warps per scheduler (measured: 92 -> 97 Gpoints/s).
-            if (!(IWB_DBG & 2) && !do_px0 && ty >= jr_lo && ty + NW <= jr_hi) {
+            if (!do_px0 && ty >= jr_lo && ty + NW <= jr_hi) {
                 const unsigned Am2 = A + o_m2;
                 const double yyA = lds_f64<0>(ya), yyB = lds_f64<NW * 8>(ya);
                 const double m2[4] = {lds_f64<0>(Am2), lds_f64<256>(Am2), lds_f64<ROWB>(Am2), lds_f64<ROWB + 256>(Am2)};
-                const bool origin = (p == P.i_zero) && (j0 - hj + ty == P.j_zero || j0 - hj + ty + NW == P.j_zero);
+                const bool origin = (p == P.i_zero) && (j0 - 2 + ty == P.j_zero || j0 - 2 + ty + NW == P.j_zero);
                 double f[4];
                 if (DT == IWB_F64) {
                     const double sA = xxp + yyA, sB = xxp + yyB;
@@ -702,8 +495,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                     const float sA = __fadd_rn((float)xxp, (float)yyA), sB = __fadd_rn((float)xxp, (float)yyB);
                     const float s[4] = {__fadd_rn(sA, (float)zz0), __fadd_rn(sA, (float)zz1),
                                         __fadd_rn(sB, (float)zz0), __fadd_rn(sB, (float)zz1)};
-                    if (DT == IWB_F32_STRICT) phi_f32strict<4>(s, (float)xp, pc, f);
-                    else phi_exact_f32ref<4, true>(s, (float)xp, pc, f, origin || !pc.prechecked);
+                    phi_exact_f32ref<4, true>(s, (float)xp, pc, f, origin || !pc.prechecked);
                 }
                 const unsigned Ap = A + o_p;
                 sts_f64<0>(Ap, f[0]); sts_f64<256>(Ap, f[1]); sts_f64<ROWB>(Ap, f[2]); sts_f64<ROWB + 256>(Ap, f[3]);
@@ -724,21 +516,19 @@ k_energy3d(const __grid_constant__ K3Params P)
                 const double yyj = lds_f64<0>(ya);
                 const double m2a = lds_f64<0>(Am2), m2b = lds_f64<256>(Am2);   // harmless when !do_px (never used)
                 double f[2];
-                if (IWB_DBG & 2) { f[0] = xxp + zz0; f[1] = xxp + zz1; }
-                else if (DT == IWB_F64) {
+                if (DT == IWB_F64) {
                     const double sxy = xxp + yyj;
                     const double s[2] = {sxy + zz0, sxy + zz1};
                     // the row through the origin (r == 0 at one lane) takes the reference flavour
-                    const bool origin_row = (p == P.i_zero) && (j0 - hj + jr == P.j_zero);
+                    const bool origin_row = (p == P.i_zero) && (j0 - 2 + jr == P.j_zero);
                     // (exotic grids / parameters fail the host's operand-range proof: reference flavour throughout)
                     if (MODE == 0) phi_exact_f64<2, true>(s, xp, pc, f, origin_row || !pc.prechecked);
                     else phi_fast_f64<2>(s, xp, pc, f, origin_row || !pc.prechecked);
                 } else {
                     const float sxy = __fadd_rn((float)xxp, (float)yyj);
                     const float s[2] = {__fadd_rn(sxy, (float)zz0), __fadd_rn(sxy, (float)zz1)};
-                    const bool origin_row = (p == P.i_zero) && (j0 - hj + jr == P.j_zero);
-                    if (DT == IWB_F32_STRICT) phi_f32strict<2>(s, (float)xp, pc, f);
-                    else phi_exact_f32ref<2, true>(s, (float)xp, pc, f, origin_row || !pc.prechecked);
+                    const bool origin_row = (p == P.i_zero) && (j0 - 2 + jr == P.j_zero);
+                    phi_exact_f32ref<2, true>(s, (float)xp, pc, f, origin_row || !pc.prechecked);
                 }
                 const unsigned Ap = A + o_p;
                 sts_f64<0>(Ap, f[0]);
@@ -778,28 +568,17 @@ k_energy3d(const __grid_constant__ K3Params P)
             constexpr int NV = 6 + 3 * NSH;    // values actually reduced
             double vals[NV];
             // E+ = (sum + sum|.|)/2 and E- = (sum - sum|.|)/2, per thread (halving is exact)
-#if IWB_SUM_RHO
-            const double half_dV = 0.5 * P.dV;
-            vals[0] = (acc_sum + acc_abs) * half_dV; vals[1] = (acc_sum - acc_abs) * half_dV;
-#else
             vals[0] = (acc_sum + acc_abs) * 0.5; vals[1] = (acc_sum - acc_abs) * 0.5;
-#endif
             vals[2] = __longlong_as_double((long long)((cnt3 >> 8) & 0xff));
             vals[3] = __longlong_as_double((long long)(cnt3 & 0xff));
             vals[4] = __longlong_as_double((long long)((cnt3 >> 16) & 0xff));   // zeros + masked columns (corrected below)
             vals[5] = __longlong_as_double(0LL);      // cnt_nan: derived by the host from the other three
 #pragma unroll
             for (int s = 0; s < NSH; ++s) {
-#if IWB_SUM_RHO
-                vals[6 + s] = (sh_sum[s] + sh_abs[s]) * half_dV;
-                vals[6 + NSH + s] = (sh_sum[s] - sh_abs[s]) * half_dV;
-#else
                 vals[6 + s] = (sh_sum[s] + sh_abs[s]) * 0.5;
                 vals[6 + NSH + s] = (sh_sum[s] - sh_abs[s]) * 0.5;
-#endif
                 vals[6 + 2 * NSH + s] = __longlong_as_double((long long)sh_cnt[s]);
             }
-#if IWB_FLUSH_PACK
             // warp butterfly (fixed order).  The counts are at most 64 per thread and 2048 per warp: two of them share a
             // 32-bit word (16-bit fields), so 3 + NSH counts cost (3 + NSH + 1) / 2 one-register shuffles per step
             // instead of 3 + NSH two-register ones.
@@ -807,17 +586,7 @@ k_energy3d(const __grid_constant__ K3Params P)
             unsigned cw[NCW];
             {
                 int c[2 * NCW];
-#if IWB_T_INT
-                // neg | NaN | zero were counted; every other output point of this thread in the interval is positive
-                int rows_out = 0;
-#pragma unroll
-                for (int jr = ty; jr < RJ; jr += NW) rows_out += (jr >= o_lo && jr <= o_hi) ? 1 : 0;
-                const int npts = npl * rows_out * (i_last - flush_from + 1);
-                c[0] = cnt3 & 0xff; c[2] = (cnt3 >> 16) & 0xff;
-                c[1] = npts - c[0] - c[2] - ((cnt3 >> 8) & 0xff);
-#else
                 c[0] = cnt3 & 0xff; c[1] = (cnt3 >> 8) & 0xff; c[2] = (cnt3 >> 16) & 0xff;     // neg, pos, zero
-#endif
 #pragma unroll
                 for (int s2 = 0; s2 < NSH; ++s2) c[3 + s2] = sh_cnt[s2];
                 if (NCNT & 1) c[NCNT] = 0;
@@ -844,19 +613,6 @@ k_energy3d(const __grid_constant__ K3Params P)
 #pragma unroll
                 for (int s2 = 0; s2 < NSH; ++s2) vals[6 + 2 * NSH + s2] = __longlong_as_double(field(3 + s2));
             }
-#else
-            // warp butterfly (fixed order), integers added as integers
-#pragma unroll
-            for (int q = 0; q < NV; ++q) {
-                const bool is_int = (q >= 2 && q < 6) || (q >= 6 + 2 * NSH);
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    double o = __shfl_xor_sync(0xffffffffu, vals[q], off);
-                    if (is_int) vals[q] = __longlong_as_double(__double_as_longlong(vals[q]) + __double_as_longlong(o));
-                    else vals[q] += o;
-                }
-            }
-#endif
             if (tx == 0) {
 #pragma unroll
                 for (int q = 0; q < NV; ++q) scratch[ty * NV + q] = vals[q];
@@ -880,20 +636,14 @@ k_energy3d(const __grid_constant__ K3Params P)
                         if (is_int) acc = __longlong_as_double(__double_as_longlong(acc) + __double_as_longlong(o));
                         else acc += o;
                     }
-#if !IWB_T_INT
                     // the zero field counted the masked (non-output) columns of every row as well
                     if (q == 4)
                         acc = __longlong_as_double(__double_as_longlong(acc) -
                                                    (long long)Tj * (RK - Tk) * (i_last - flush_from + 1));
-#endif
                 }
                 P.partial[((size_t)fb * ntiles + rnk) * ROW + slot] = acc;     // slot of the tile's schedule index
             }
-#if IWB_NBSYNC
-            __syncthreads();     // warps drift: without a CTA-wide step barrier the scratch needs its own guard before reuse
-#else
             // the scratch is rewritten at the next flush only, at least one step barrier from here
-#endif
             acc_sum = 0.0; acc_abs = 0.0; cnt3 = 0;
             flush_from = i_last + 1;
 #pragma unroll
@@ -903,7 +653,7 @@ k_energy3d(const __grid_constant__ K3Params P)
         auto runP = [&](int p, int s3, double xp, double xxp) { taskP(p, s3, xp, xxp); };
         auto runC = [&](int q, int s3) { stepOC(false, 0, 0.0, true, q, s3); };
         // O(i) followed by C(i+1) (the latter when doC)
-        auto runOC = [&](int i, double xxi, bool doC, int m3p1) { stepOC(!(IWB_DBG & 1), i, xxi, doC, i + 1, m3p1); };
+        auto runOC = [&](int i, double xxi, bool doC, int m3p1) { stepOC(true, i, xxi, doC, i + 1, m3p1); };
         // phi_x(n0-1) may be written once every phi plane exists and its ring slot (that of phi_x(n0-5),
         // last read by O(n0-4)) is dead, i.e. from the step of output plane n0-3 on; it is first needed
         // by O(n0-2) (n0 == 3: by every plane, and 0 >= n0-3 holds).

@@ -52,8 +52,6 @@ static cudaError_t launch_nsh(int nshell, int cfg, const K3Params& P, int sm_cou
     return launch_cfg<DT, IWB_MAX_SHELLS, EMIT, MODE>(cfg, P, sm_count, st);
 }
 
-// defined in energy3d_f32.cu (IWB_F32_STRICT)
-cudaError_t launch_k3_f32strict(int nshell, bool emit, int cfg, const K3Params& P, int sm_count, cudaStream_t st);
 // defined in energy3d_fast.cu (IWB_MODE_FAST, float64 only)
 cudaError_t launch_k3_fast(int nshell, bool emit, int cfg, const K3Params& P, int sm_count, cudaStream_t st);
 

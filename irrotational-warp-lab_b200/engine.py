@@ -59,11 +59,10 @@ class Engine:
         if len(shells) > _capi.MAX_SHELLS:
             raise ValueError(f"at most {_capi.MAX_SHELLS} shell radii per call")
         p = _capi.Params3D()
-        if dtype not in ("float64", "float32", "float32_strict"):
-            raise ValueError(f"Unknown dtype: {dtype!r} (expected: float64|float32|float32_strict)")
-        # "float32" is the reference's --dtype float32 as NumPy >= 2 evaluates it (mixed precision, bit for bit);
-        # "float32_strict" evaluates phi entirely in float32 on the FP32 pipe (no reference semantics, tolerance only)
-        p.dtype = {"float64": _capi.F64, "float32": _capi.F32_REF, "float32_strict": _capi.F32_STRICT}[dtype]
+        if dtype not in ("float64", "float32"):
+            raise ValueError(f"Unknown dtype: {dtype!r} (expected: float64|float32)")
+        # "float32" is the reference's --dtype float32 as NumPy >= 2 evaluates it (mixed precision), bit for bit
+        p.dtype = _capi.F32_REF if dtype == "float32" else _capi.F64
         if mode not in ("exact", "fast"):
             raise ValueError(f"Unknown mode: {mode!r} (expected: exact|fast)")
         p.mode = _capi.MODE_FAST if mode == "fast" else _capi.MODE_EXACT
@@ -203,7 +202,7 @@ class Engine:
         if len(shells) > _capi.MAX_SHELLS:
             raise ValueError(f"at most {_capi.MAX_SHELLS} shell radii per call")
         if dtype not in ("float64", "float32"):
-            raise ValueError(f"Unknown dtype: {dtype!r} (expected: float64|float32; float32_strict exists for the 3D evaluator only)")
+            raise ValueError(f"Unknown dtype: {dtype!r} (expected: float64|float32)")
         p = _capi.ParamsAxisym()
         p.dtype = _capi.F32_REF if dtype == "float32" else _capi.F64
         p.mode = _capi.MODE_EXACT
