@@ -9,8 +9,12 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# IWB_LIB names another build of the same library in this directory (A/B timing of kernel variants; development aid)
-LIB_PATH = os.path.join(_HERE, os.path.basename(os.environ.get("IWB_LIB", "libiwb200.so")))
+# The product library.  A/B timing of kernel variants (scripts/ab2.sh) loads another build of it from this directory, named
+# by IWB_LIB -- honoured only together with IWB_ALLOW_LIB_OVERRIDE=1, so that a stray environment variable cannot swap the
+# library under the tests or the benchmark (bench.py refuses to run with an override).
+_override = os.environ.get("IWB_LIB") if os.environ.get("IWB_ALLOW_LIB_OVERRIDE") == "1" else None
+LIB_PATH = os.path.join(_HERE, os.path.basename(_override or "libiwb200.so"))
+LIB_IS_OVERRIDDEN = _override is not None
 
 MAX_SHELLS = 8
 FLUSH_PLANES = 16

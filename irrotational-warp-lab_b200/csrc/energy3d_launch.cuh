@@ -19,12 +19,20 @@ static cudaError_t launch_one(const K3Params& P, int sm_count, cudaStream_t st)
 {
     auto kern = k_energy3d<DT, NSH, RJ, NW, EMIT, MINB, MODE>;
     constexpr size_t smem = Geo<RJ, NW>::SMEM_BYTES;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // attribute and occupancy are properties of (instantiation, device): asked once per device, not per launch
+    static int per_sm_cached[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    int per_sm = (dev >= 0 && dev < 64) ? per_sm_cached[dev] : 0;
+    if (per_sm == 0) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        if (dev >= 0 && dev < 64) per_sm_cached[dev] = per_sm;
+    }
     int grid = sm_count * per_sm;
     if (grid > P.nspans) grid = P.nspans;
     kern<<<grid, NW * 32, smem, st>>>(P);

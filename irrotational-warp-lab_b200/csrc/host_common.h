@@ -108,6 +108,8 @@ struct iwb_handle {
     iwb::Scratch scr[iwb::NSCRATCH];
     iwb::AsyncSlot aslot[iwb::NASYNC];
     int next_aslot = 0;
+    void* prep = nullptr;      // iwb::PrepCache (energy3d.cu): the last few host preparations, see prepare_host
+    void (*prep_free)(void*) = nullptr;
     int k3_config = 0;         // kernel geometry variant (IWB_K3_CONFIG env override)
     int k3_static_pct = -1;    // share of the work units handed out as one large span per CTA; -1 = automatic (80 / 70 %),
                                // IWB_K3_STATIC_PCT env override
@@ -117,6 +119,8 @@ namespace iwb {
 AxisCoef make_axis_coef(double h);
 double shell_threshold_f64(double R);
 double shell_threshold_f32(double R);
+double bin_threshold_f64(double e);
+double bin_threshold_f32(double e);
 PhiConst make_phi_const(double rho, double sigma, double v, double eps, double sinh_rs, double cosh_rs);
 bool phi_fast_path_is_safe(const double* const coords[3], const int n[3], double rho, double sigma, double v, double eps,
                            double sinh_rs, double cosh_rs, int zero_index[3], bool float32_grid);

@@ -4,6 +4,6 @@ out=gpurun_out/ab_quick.log
 : > $out
 for lib in "$@"; do
   echo "=== $lib" >> $out
-  IWB_LIB=$lib python scripts/k3_probe.py 1024 5 float64 0 128 >> $out 2>&1
+  IWB_ALLOW_LIB_OVERRIDE=1 IWB_LIB=$lib python scripts/k3_probe.py 1024 5 float64 0 128 >> $out 2>&1
 done
 cat $out
