@@ -754,11 +754,11 @@ int iwb_radial_profile3d(iwb_handle* h, const iwb_params3d* p, const iwb_profile
     const int nfb_total = (p->n0 + FLUSH - 1) / FLUSH;
     const int fb0 = p->i_begin / FLUSH, fb1 = (p->i_end + FLUSH - 1) / FLUSH;
 
-    // device: edges[nb+1] | slo[nb+1] | part_sum[nfb][SUB][nb] | part_cnt[...] | sum[nb] | cnt[nb]
+    // device: edges[nb+1] | slo[nb+1] | part_sum[nfb][SUB][nb] | part_cnt[...] | sum[nb] | cnt[nb] | fb_sum[nfb][nb] | fb_cnt[nfb][nb]
     const size_t npart = (size_t)nfb_total * PROF_SUB * nb;
     const size_t off_slo = (size_t)nb + 1, off_psum = 2 * ((size_t)nb + 1), off_pcnt = off_psum + npart, off_sum = off_pcnt + npart,
-                 off_cnt = off_sum + nb;
-    IWB_CUDA(c.prof.reserve((off_cnt + nb) * sizeof(double)));
+                 off_cnt = off_sum + nb, off_fsum = off_cnt + nb, off_fcnt = off_fsum + (size_t)nfb_total * nb;
+    IWB_CUDA(c.prof.reserve((off_fcnt + (size_t)nfb_total * nb) * sizeof(double)));
     IWB_CUDA(c.h_prof.reserve(((size_t)3 * nb + 2) * sizeof(double)));
     IWB_CUDA(c.rho.reserve((size_t)pass * plane_bytes));
     IWB_CUDA(c.table.reserve((size_t)nfb_total * ROW * sizeof(double)));
@@ -809,8 +809,10 @@ int iwb_radial_profile3d(iwb_handle* h, const iwb_params3d* p, const iwb_profile
         }
         IWB_CUDA(cudaGetLastError());
     }
-    k_radial_reduce<<<(nb + 63) / 64, 64, 0, st>>>(dprof + off_psum, (const long long*)(dprof + off_pcnt), fb0, fb1, nb,
-                                                   dprof + off_sum, (long long*)(dprof + off_cnt));
+    k_radial_reduce_sub<<<fb1 - fb0, 64, 0, st>>>(dprof + off_psum, (const long long*)(dprof + off_pcnt), fb0, nb,
+                                                  dprof + off_fsum, (long long*)(dprof + off_fcnt));
+    k_radial_reduce_fb<<<(nb + 63) / 64, 64, 0, st>>>(dprof + off_fsum, (const long long*)(dprof + off_fcnt), fb0, fb1, nb,
+                                                      dprof + off_sum, (long long*)(dprof + off_cnt));
     IWB_CUDA(cudaGetLastError());
     k_reduce_rows<<<1, 128, 0, st>>>((const double*)c.table.p + (size_t)fb0 * ROW, (double*)c.out.p, fb1 - fb0);
     IWB_CUDA(cudaGetLastError());

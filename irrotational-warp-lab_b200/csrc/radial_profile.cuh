@@ -191,17 +191,17 @@ static __global__ void __launch_bounds__(PROF_FAST_NW * 32) k_radial_hist_fast(c
     }
 }
 
-// flush blocks [fb0, fb1) x PROF_SUB partials -> [nb], in index order
-static __global__ void k_radial_reduce(const double* __restrict__ part_sum, const long long* __restrict__ part_cnt,
-                                       int fb0, int fb1, int nb, double* __restrict__ sum, long long* __restrict__ cnt)
+// partials [flush block][PROF_SUB][nb] -> [nb]: first the PROF_SUB CTAs of every flush block in index order (one block per
+// flush block, one thread per bin), then the flush blocks in index order.  Two short dependent chains (64 + nfb additions per
+// bin) instead of round 1's single one of 64 x nfb, which took 0.6 ms at n = 1024; the order is fixed either way.
+static __global__ void k_radial_reduce_sub(const double* __restrict__ part_sum, const long long* __restrict__ part_cnt,
+                                           int fb0, int nb, double* __restrict__ fb_sum, long long* __restrict__ fb_cnt)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nb) return;
-    double a = 0.0;
-    long long c = 0;
-    // PROF_SUB loads in flight, then added in index order (the order is what makes the result reproducible)
-    for (int fb = fb0; fb < fb1; ++fb) {
+    const int fb = fb0 + blockIdx.x;
+    for (int q = threadIdx.x; q < nb; q += blockDim.x) {
         const size_t s0 = (size_t)fb * PROF_SUB;
+        double a = 0.0;
+        long long c = 0;
         for (int u = 0; u < PROF_SUB; u += 16) {
             double v[16];
             long long w[16];
@@ -210,7 +210,19 @@ static __global__ void k_radial_reduce(const double* __restrict__ part_sum, cons
 #pragma unroll
             for (int e = 0; e < 16; ++e) { a += v[e]; c += w[e]; }
         }
+        fb_sum[(size_t)fb * nb + q] = a;
+        fb_cnt[(size_t)fb * nb + q] = c;
     }
+}
+
+static __global__ void k_radial_reduce_fb(const double* __restrict__ fb_sum, const long long* __restrict__ fb_cnt,
+                                          int fb0, int fb1, int nb, double* __restrict__ sum, long long* __restrict__ cnt)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nb) return;
+    double a = 0.0;
+    long long c = 0;
+    for (int fb = fb0; fb < fb1; ++fb) { a += fb_sum[(size_t)fb * nb + q]; c += fb_cnt[(size_t)fb * nb + q]; }
     sum[q] = a;
     cnt[q] = c;
 }
