@@ -21,6 +21,8 @@ from .backend import BACKEND_NAME, EPS, _ShellClosure, _grid, summary_metrics
 from .engine import get_engine
 
 
+_GRIDS: dict = {}            # (extent, n, dtype) -> (linspace axis, spacing): read-only
+_PREPARED: dict = {}         # (peer group, parameters) -> ((iwb_params3d, arrays it points into), device result row)
 _PEER_GROUPS: dict = {}      # (process group, device) -> PeerGroup, or None when the peer exchange is unavailable
 PEER_NFB_DEFAULT = 256       # flush blocks the peer buffers are sized for (n <= 4096); grown on demand
 
@@ -70,7 +72,12 @@ def compute_energy_3d_sharded(*, rho, sigma, v, extent, n, dtype="float64", shel
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
     eng = get_engine(dev.index)
-    x, dx = _grid(-extent, extent, n, dtype)
+    gkey = (float(extent), int(n), dtype)
+    if gkey not in _GRIDS:
+        if len(_GRIDS) >= 16:
+            _GRIDS.clear()
+        _GRIDS[gkey] = _grid(-extent, extent, n, dtype)
+    x, dx = _GRIDS[gkey]
     shells = [8.0 * rho, 12.0 * rho] if shells is None else [float(s) for s in shells]
     if shard not in ("auto", "tiles", "slab"):
         raise ValueError(f"Unknown shard mode: {shard!r} (expected: auto|tiles|slab)")
@@ -89,14 +96,22 @@ def compute_energy_3d_sharded(*, rho, sigma, v, extent, n, dtype="float64", shel
         nfb = sharding.num_flush_blocks(n)
         stride, first = tiles
         if peers is not None:
-            row = torch.empty(ROW_WIDTH, dtype=torch.float64, device=dev)
-            stream = torch.cuda.current_stream(dev)
-            keep = peers.energy3d_tiles_exchange_async(row.data_ptr(), stream.cuda_stream, x=x, y=x, z=x, dx=dx, dy=dx, dz=dx,
-                                                       rho=rho, sigma=sigma, v=v, dtype=dtype, shells=radii, eps=EPS)
-            res = eng.read_row(row.data_ptr(), len(radii), stream.cuda_stream)
+            # the parameter block and the result row of a repeated evaluation are kept (a strong-scaling step is ~1 ms
+            # on eight GPUs: 15 us of host work per call count); the coordinates still travel to the device every call
+            key = (peers.rank, peers.world, eng.device, float(rho), float(sigma), float(v), float(extent), int(n), dtype, tuple(radii))
+            hit = _PREPARED.get(key)
+            if hit is None:
+                if len(_PREPARED) >= 16:
+                    _PREPARED.clear()
+                hit = _PREPARED[key] = (peers.prepare(x=x, y=x, z=x, dx=dx, dy=dx, dz=dx, rho=rho, sigma=sigma, v=v, dtype=dtype,
+                                                      shells=radii, eps=EPS),
+                                        torch.empty(ROW_WIDTH, dtype=torch.float64, device=dev))
+            (params, _keep), row = hit
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            peers.run_prepared(params, row.data_ptr(), stream)
+            res = eng.read_row(row.data_ptr(), len(radii), stream)
             res["cnt_nan"] = n ** 3 - res["cnt_pos"] - res["cnt_neg"] - res["cnt_zero"]
             sharding.apply_reference_nonfinite(res)
-            del keep
             return res
         local = torch.empty((nfb, TILE_CHAINS // stride, ROW_WIDTH), dtype=torch.float64, device=dev)   # fully written
         stream = torch.cuda.current_stream(dev)

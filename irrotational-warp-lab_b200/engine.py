@@ -326,10 +326,18 @@ class PeerGroup:
 
     def energy3d_tiles_exchange_async(self, row_ptr, stream_ptr=None, **kw):
         """Collective: kernel + peer push of the chain sums + combine; the result row lands in ``row_ptr`` (device)."""
-        p, keep = Engine.make_params3d(tile_stride=self.world, tile_first=self.rank, **kw)
+        p, keep = self.prepare(**kw)
+        self.run_prepared(p, row_ptr, stream_ptr)
+        return keep
+
+    def prepare(self, **kw):
+        """This rank's ``iwb_params3d`` of a tile-sharded evaluation (and the arrays it points into): a caller that repeats
+        an evaluation keeps the pair and calls :meth:`run_prepared`."""
+        return Engine.make_params3d(tile_stride=self.world, tile_first=self.rank, **kw)
+
+    def run_prepared(self, p, row_ptr, stream_ptr=None):
         _capi.check(self._eng._lib.iwb_energy3d_tiles_exchange_async(self._eng._h, self._h, C.byref(p),
                                                                      C.c_void_p(int(stream_ptr or 0)), C.c_void_p(int(row_ptr))))
-        return keep
 
     def close(self):
         if self._h:
