@@ -110,7 +110,9 @@ typedef struct {
 /* Fixed-layout partial sums of one slab, for the shard-count-independent reduction:
  * one row per "flush block" of IWB_FLUSH_PLANES planes of axis 0, IWB_ROW_WIDTH doubles per row
  * (int64 counts are stored bit-cast in double slots).  See DESIGN.md §5. */
+#ifndef IWB_FLUSH_PLANES
 #define IWB_FLUSH_PLANES 16
+#endif
 #define IWB_ROW_WIDTH (6 + 3 * IWB_MAX_SHELLS)   /* e_pos e_neg cnt_pos cnt_neg cnt_zero cnt_nan | shell_pos[8] shell_neg[8] shell_cnt[8] */
 
 int iwb_version(void);

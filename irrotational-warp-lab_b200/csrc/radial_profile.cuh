@@ -191,6 +191,95 @@ static __global__ void __launch_bounds__(PROF_FAST_NW * 32) k_radial_hist_fast(c
     }
 }
 
+// ---- run-length flavour (n_bins <= PROF_FAST_BINS): the default ---------------------------------------------------------
+// The lane-private kernel above is latency-bound (200 KB of bins leave 10 warps per SM; ncu: issue slots 27 % busy, a chain
+// of dependent shared-memory read-modify-writes per lane; 1.19 ms per GiB = 0.9 TB/s).  Here a lane walks a CONTIGUOUS
+// chunk of the row (columns [l * c, (l + 1) * c)), where r changes by at most dz per step, so its bin changes about once in
+// bin_width / dz points: the lane keeps the current bin, that bin's two thresholds and the running (sum, count) in
+// registers and touches nothing else until the bin changes.  Then the finished run is handed to the warp's histogram --
+// 64 x 12 bytes of shared memory per warp, so an SM holds 64 warps -- in a fixed order: points in walking order, lanes in
+// ascending order within a step, and the runs still open at the end of the CTA's rows in lane order.  Same bits on every
+// run; warps / CTAs / flush blocks are added in index order as before.
+constexpr int PROF_RLE_NW = 8;
+
+static __global__ void __launch_bounds__(PROF_RLE_NW * 32) k_radial_hist_rle(const ProfFastParams P)
+{
+    __shared__ double s_slo[PROF_FAST_BINS + 2];
+    __shared__ double s_sum[PROF_RLE_NW][PROF_FAST_BINS];
+    __shared__ int s_cnt[PROF_RLE_NW][PROF_FAST_BINS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = P.nb;
+    for (int q = threadIdx.x; q <= nb; q += blockDim.x) s_slo[q] = P.slo[q];
+    for (int q = lane; q < PROF_FAST_BINS; q += 32) { s_sum[warp][q] = 0.0; s_cnt[warp][q] = 0; }
+    __syncthreads();
+
+    const int sub = blockIdx.x;
+    const int fb = P.i_begin / FLUSH + blockIdx.y;
+    const int ia = fb * FLUSH, ib = min(ia + FLUSH, P.i_end);
+    const int nrows = (ib - ia) * P.n1;
+    const bool f64 = (P.dtype == IWB_F64);
+    const int chunk = (P.n2 + 31) / 32;
+    const int c0 = lane * chunk, c1 = min(c0 + chunk, P.n2);
+
+    // the open run of this lane: bin cur (-1: none; nb: "in no bin"), its thresholds lo <= s < hi, and what it holds
+    int cur = -1, run_cnt = 0;
+    double lo = 0.0, hi = -1.0, run_sum = 0.0;
+    // hand the runs of the lanes in `mask` to the warp's histogram, lowest lane first (fixed order)
+    auto hand_over = [&](unsigned mask, int b_out, double v_out, int c_out) {
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            const int b = __shfl_sync(0xffffffffu, b_out, src);
+            const double v = __shfl_sync(0xffffffffu, v_out, src);
+            const int c = __shfl_sync(0xffffffffu, c_out, src);
+            if (lane == 0) { s_sum[warp][b] += v; s_cnt[warp][b] += c; }
+            mask &= mask - 1;
+        }
+    };
+    for (int row = sub * PROF_RLE_NW + warp; row < nrows; row += PROF_SUB * PROF_RLE_NW) {
+        const int i = ia + row / P.n1, j = row - (row / P.n1) * P.n1;
+        const double* src = P.rho + ((size_t)(i - P.i_begin) * P.n1 + j) * P.n2;
+        const double sxy = P.xx[i] + P.yy[j];
+        const float sxy_f = __fadd_rn((float)P.xx[i], (float)P.yy[j]);
+        for (int u = 0; u < chunk; ++u) {                        // warp-uniform trip count
+            const int k = c0 + u;
+            const bool valid = k < c1;
+            double v = 0.0, s = 0.0;
+            if (valid) {
+                v = src[k];                                      // 32-byte sectors are shared by four consecutive steps (L1)
+                const double zz = P.zz[k];
+                s = f64 ? sxy + zz : (double)__fadd_rn(sxy_f, (float)zz);
+            }
+            const bool same = valid && s >= lo && s < hi;        // still inside the open run's bin
+            int b_out = 0, c_out = 0;
+            double v_out = 0.0;
+            if (valid && !same) {
+                // close the open run, find the bin of s against the thresholds (exactly the reference's masks), open a new one
+                b_out = cur; v_out = run_sum; c_out = run_cnt;
+                int kb = (cur < 0) ? 0 : min(cur, nb - 1);
+                while (kb > 0 && s < s_slo[kb]) --kb;
+                while (kb < nb && s >= s_slo[kb + 1]) ++kb;
+                if (s < s_slo[0]) { cur = nb; lo = -INFINITY; hi = s_slo[0]; }            // below the first edge: in no bin
+                else if (kb >= nb) { cur = nb; lo = s_slo[nb]; hi = INFINITY; }             // on / beyond the last edge
+                else { cur = kb; lo = s_slo[kb]; hi = s_slo[kb + 1]; }
+                run_sum = 0.0; run_cnt = 0;
+            }
+            if (valid) { run_sum += v; ++run_cnt; }
+            const unsigned mask = __ballot_sync(0xffffffffu, valid && !same && c_out > 0 && b_out >= 0 && b_out < nb);
+            if (mask) hand_over(mask, b_out, v_out, c_out);
+        }
+    }
+    hand_over(__ballot_sync(0xffffffffu, run_cnt > 0 && cur >= 0 && cur < nb), cur, run_sum, run_cnt);
+    __syncthreads();
+    for (int q = threadIdx.x; q < nb; q += blockDim.x) {
+        double a = s_sum[0][q];
+        long long c = s_cnt[0][q];
+        for (int w = 1; w < PROF_RLE_NW; ++w) { a += s_sum[w][q]; c += s_cnt[w][q]; }
+        const size_t o = ((size_t)fb * PROF_SUB + sub) * nb + q;
+        P.part_sum[o] = a;
+        P.part_cnt[o] = c;
+    }
+}
+
 // partials [flush block][PROF_SUB][nb] -> [nb]: first the PROF_SUB CTAs of every flush block in index order (one block per
 // flush block, one thread per bin), then the flush blocks in index order.  Two short dependent chains (64 + nfb additions per
 // bin) instead of round 1's single one of 64 x nfb, which took 0.6 ms at n = 1024; the order is fixed either way.

@@ -90,10 +90,13 @@ def sweep_velocity(*, mode: str, rho: float, sigma: float, v_values: list, exten
                     shells=[r1, r2], eps=EPS) for q in mine]
         results = get_engine().energy3d_batch(pts) if pts else []
         elapsed = (time.perf_counter() - t0) / max(len(mine), 1)
-        for q, res in zip(mine, results):
-            records[q] = _sweep_record(v_values[q], res["shell_pos"][0], res["shell_neg"][0],
-                                       res["shell_pos"][1], res["shell_neg"][1], r1, r2, elapsed)
-    if world > 1:
+        shell_sums = {q: [res["shell_pos"][0], res["shell_neg"][0], res["shell_pos"][1], res["shell_neg"][1], elapsed]
+                      for q, res in zip(mine, results)}
+        if world > 1:       # one all-gather of 5 doubles per point; every rank then forms every record
+            shell_sums = _gather_values(shell_sums, len(v_values), 5, group)
+        for q, (p1, n1, p2, n2, dt) in shell_sums.items():
+            records[q] = _sweep_record(v_values[q], p1, n1, p2, n2, r1, r2, dt)
+    if world > 1 and mode == "axisym":
         records = _gather_records(records, group)
     return {
         "sweep_results": [records[q] for q in range(len(v_values))],
@@ -109,6 +112,24 @@ def _dist_ready() -> bool:
         return dist.is_available() and dist.is_initialized()
     except Exception:
         return False
+
+
+def _gather_values(values: dict, npoints: int, width: int, group=None) -> dict:
+    """``{point index: [width floats]}`` of this rank's round-robin share -> the same for all points, on every rank, with
+    one ``all_gather_into_tensor`` (device tensors under NCCL, host tensors under gloo)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rows = max(-(-npoints // world), 1)
+    local = torch.full((rows, width), float("nan"), dtype=torch.float64)
+    for q, vals in values.items():
+        local[q // world] = torch.tensor(vals, dtype=torch.float64)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    local = local.to(dev)
+    full = torch.empty((world, rows, width), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(full.view(-1), local.view(-1), group=group)
+    full = full.cpu()
+    return {q: [float(t) for t in full[q % world, q // world]] for q in range(npoints)}
 
 
 def _gather_records(records: dict, group=None) -> dict:

@@ -57,6 +57,9 @@ def _worker(rank, world, port, out_path):
         mine = sweeps.partition_points(7, rank, world)
         merged = sweeps._gather_records({q: {"v": float(q), "rank": rank} for q in mine})
         assert sorted(merged) == list(range(7)) and all(merged[q]["rank"] == q % world for q in merged)
+        vals = sweeps._gather_values({q: [float(q), 10.0 * q + rank, -1.5] for q in mine}, 7, 3)
+        assert vals == {q: [float(q), 10.0 * q + q % world, -1.5] for q in range(7)}
+        assert sweeps._gather_values({}, 0, 3) == {}
         if rank == 0:
             res["table_hex"] = [float(v).hex() for v in full.numpy().reshape(-1)]
             json.dump(res, open(out_path, "w"))
