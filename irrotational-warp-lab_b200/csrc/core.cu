@@ -56,29 +56,6 @@ double shell_threshold_f32(double R)
     return (double)s;
 }
 
-// Smallest s with RN(sqrt(s)) >= e: the reference's bin mask R >= e[k] (tail.py:75) applied to s = (x*x + y*y) + z*z before
-// the square root (RN(sqrt) is monotone).  e <= 0 admits every s >= 0.
-double bin_threshold_f64(double e)
-{
-    if (!(e > 0.0)) return 0.0;
-    if (isinf(e)) return INFINITY;
-    double s = e * e;
-    while (s > 0.0 && sqrt(nextafter(s, -INFINITY)) >= e) s = nextafter(s, -INFINITY);
-    while (sqrt(s) < e) s = nextafter(s, INFINITY);
-    return s;
-}
-
-// float32 grid: s and r are float32, the comparison with the (float64) edge is made on the widened r
-double bin_threshold_f32(double e)
-{
-    if (!(e > 0.0)) return 0.0;
-    if (!(e < 3.0e38)) return INFINITY;
-    float s = (float)(e * e);
-    while (s > 0.0f && (double)sqrtf(nextafterf(s, -INFINITY)) >= e) s = nextafterf(s, -INFINITY);
-    while ((double)sqrtf(s) < e) s = nextafterf(s, INFINITY);
-    return (double)s;
-}
-
 // true when |v| is +0 or 2^lo <= |v| <= 2^hi
 static bool zero_or_in_range(double v, int lo, int hi)
 {

@@ -754,9 +754,9 @@ int iwb_radial_profile3d(iwb_handle* h, const iwb_params3d* p, const iwb_profile
     const int nfb_total = (p->n0 + FLUSH - 1) / FLUSH;
     const int fb0 = p->i_begin / FLUSH, fb1 = (p->i_end + FLUSH - 1) / FLUSH;
 
-    // device: edges[nb+1] | slo[nb+1] | part_sum[nfb][SUB][nb] | part_cnt[...] | sum[nb] | cnt[nb] | fb_sum[nfb][nb] | fb_cnt[nfb][nb]
+    // device: edges[nb+1] | part_sum[nfb][SUB][nb] | part_cnt[...] | sum[nb] | cnt[nb] | fb_sum[nfb][nb] | fb_cnt[nfb][nb]
     const size_t npart = (size_t)nfb_total * PROF_SUB * nb;
-    const size_t off_slo = (size_t)nb + 1, off_psum = 2 * ((size_t)nb + 1), off_pcnt = off_psum + npart, off_sum = off_pcnt + npart,
+    const size_t off_psum = (size_t)nb + 1, off_pcnt = off_psum + npart, off_sum = off_pcnt + npart,
                  off_cnt = off_sum + nb, off_fsum = off_cnt + nb, off_fcnt = off_fsum + (size_t)nfb_total * nb;
     IWB_CUDA(c.prof.reserve((off_fcnt + (size_t)nfb_total * nb) * sizeof(double)));
     IWB_CUDA(c.h_prof.reserve(((size_t)3 * nb + 2) * sizeof(double)));
@@ -767,12 +767,7 @@ int iwb_radial_profile3d(iwb_handle* h, const iwb_params3d* p, const iwb_profile
     double* dprof = (double*)c.prof.p;
     double* hprof = (double*)c.h_prof.p;
     memcpy(hprof, prof->edges, ((size_t)nb + 1) * sizeof(double));
-    // thresholds on s = r*r for the fast flavour (up to PROF_FAST_BINS bins): bin k <=> slo[k] <= s < slo[k+1]
-    const bool fast = nb <= PROF_FAST_BINS && prof_fast_points_per_lane(p->n1, p->n2) <= 60000;
-    for (int q = 0; q <= nb; ++q)
-        hprof[off_slo + q] = (p->dtype == IWB_F64) ? bin_threshold_f64(prof->edges[q]) : bin_threshold_f32(prof->edges[q]);
-    IWB_CUDA(cudaMemcpyAsync(dprof, hprof, 2 * ((size_t)nb + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (fast) IWB_CUDA(cudaFuncSetAttribute(k_radial_hist_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROF_FAST_SMEM));
+    IWB_CUDA(cudaMemcpyAsync(dprof, hprof, ((size_t)nb + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
 
     IWB_CUDA(cudaEventRecord(c.ev0, st));
     for (int ia = p->i_begin; ia < p->i_end; ia += pass) {
@@ -785,28 +780,15 @@ int iwb_radial_profile3d(iwb_handle* h, const iwb_params3d* p, const iwb_profile
         if (rc) return rc;
         rc = launch_slab(h, L, (double*)c.table.p, st);
         if (rc) return rc;
-        if (fast) {
-            ProfFastParams R;
-            R.rho = (const double*)c.rho.p;
-            R.xx = L.P.xx; R.yy = L.P.yy; R.zz = L.P.zz;
-            R.slo = dprof + off_slo;
-            R.n1 = p->n1; R.n2 = p->n2; R.i_begin = q.i_begin; R.i_end = q.i_end; R.nb = nb; R.dtype = p->dtype;
-            R.e0 = (float)prof->edges[0];
-            R.inv_width = (float)((double)nb / (prof->edges[nb] - prof->edges[0]));     // finite and >= 0
-            R.part_sum = dprof + off_psum;
-            R.part_cnt = (long long*)(dprof + off_pcnt);
-            k_radial_hist_fast<<<dim3(PROF_SUB, L.fb1 - L.fb0), PROF_FAST_NW * 32, PROF_FAST_SMEM, st>>>(R);
-        } else {
-            ProfParams R;
-            R.rho = (const double*)c.rho.p;
-            R.xx = L.P.xx; R.yy = L.P.yy; R.zz = L.P.zz;
-            R.edges = dprof;
-            R.n1 = p->n1; R.n2 = p->n2; R.i_begin = q.i_begin; R.i_end = q.i_end; R.nb = nb; R.dtype = p->dtype;
-            R.inv_width = (double)nb / (prof->edges[nb] - prof->edges[0]);     // finite and > 0 (an overflowing span gives 0)
-            R.part_sum = dprof + off_psum;
-            R.part_cnt = (long long*)(dprof + off_pcnt);
-            k_radial_hist<<<dim3(PROF_SUB, L.fb1 - L.fb0), PROF_NW * 32, 0, st>>>(R);
-        }
+        ProfParams R;
+        R.rho = (const double*)c.rho.p;
+        R.xx = L.P.xx; R.yy = L.P.yy; R.zz = L.P.zz;
+        R.edges = dprof;
+        R.n1 = p->n1; R.n2 = p->n2; R.i_begin = q.i_begin; R.i_end = q.i_end; R.nb = nb; R.dtype = p->dtype;
+        R.inv_width = (double)nb / (prof->edges[nb] - prof->edges[0]);     // finite and > 0 (an overflowing span gives 0)
+        R.part_sum = dprof + off_psum;
+        R.part_cnt = (long long*)(dprof + off_pcnt);
+        k_radial_hist<<<dim3(PROF_SUB, L.fb1 - L.fb0), PROF_NW * 32, 0, st>>>(R);
         IWB_CUDA(cudaGetLastError());
     }
     k_radial_reduce_sub<<<fb1 - fb0, 64, 0, st>>>(dprof + off_psum, (const long long*)(dprof + off_pcnt), fb0, nb,

@@ -119,8 +119,6 @@ namespace iwb {
 AxisCoef make_axis_coef(double h);
 double shell_threshold_f64(double R);
 double shell_threshold_f32(double R);
-double bin_threshold_f64(double e);
-double bin_threshold_f32(double e);
 PhiConst make_phi_const(double rho, double sigma, double v, double eps, double sinh_rs, double cosh_rs);
 bool phi_fast_path_is_safe(const double* const coords[3], const int n[3], double rho, double sigma, double v, double eps,
                            double sinh_rs, double cosh_rs, int zero_index[3], bool float32_grid);

@@ -8,6 +8,11 @@
 // and PROF_NW warps by row index; every warp owns a private histogram that only its lane 0 updates, one bin at a time
 // (the lanes of one bin are added by a fixed shuffle tree); warps, CTAs and flush blocks are then added in index
 // order.  The result therefore depends neither on scheduling nor on how the planes were cut into passes or slabs.
+//
+// Round 2 built and measured two replacements for k_radial_hist -- lane-private histograms with thresholds on s instead of
+// a square root (200 KB of shared memory, 10 warps per SM: latency-bound, 1.19 ms per GiB), and per-lane run-length
+// accumulation over contiguous chunks of a row (the strided loads cost 32 wavefronts each: 1.45 ms per GiB) -- against
+// 1.08 ms per GiB for this kernel; neither is in the source (profiles/r2_f_rows_probe.log, git history).
 #pragma once
 #include "energy3d.cuh"
 
@@ -81,199 +86,6 @@ static __global__ void __launch_bounds__(PROF_NW * 32) k_radial_hist(const ProfP
         double a = s_sum[0][q];
         long long c = s_cnt[0][q];
         for (int w = 1; w < PROF_NW; ++w) { a += s_sum[w][q]; c += s_cnt[w][q]; }
-        const size_t o = ((size_t)fb * PROF_SUB + sub) * nb + q;
-        P.part_sum[o] = a;
-        P.part_cnt[o] = c;
-    }
-}
-
-// ---- the fast flavour (n_bins <= PROF_FAST_BINS): lane-private histograms, thresholds on s instead of a square root ----
-// Round 1's kernel above spends ~10 ms on the 8.6 GB of an n = 1024^3 field (0.86 TB/s): a float64 sqrt per point and, per
-// group of 32 points, one ballot + 10-shuffle reduction for every bin present in the group.  Here
-//   * bin k is decided on s = (x*x + y*y) + z*z itself:  slo[k] <= s < slo[k+1]  with  slo[k] = min{s : RN(sqrt(s)) >= e[k]}
-//     found by the host (the same points as the reference's masks (R >= e[k]) & (R < e[k+1]), tail.py:75; a float32 sqrt
-//     only supplies the first guess), and
-//   * every LANE owns a private histogram in shared memory ([warp][bin][lane]: conflict-free for any mix of bins), so a
-//     point is one shared-memory read-modify-write of its sum and one of its 16-bit count, and no lane talks to another
-//     (a first version counted with shared-memory atomics: 32 lanes on one address, no faster than round 1's kernel).
-//     The lanes of a warp are folded by a fixed shuffle tree at the end, warps / CTAs / flush blocks in index order as
-//     before: same bits on every run, for every pass size and slab decomposition.
-constexpr int PROF_FAST_BINS = 64;
-constexpr int PROF_FAST_NW = 10;       // 10 x 64 x 32 lane-private (double sum, 16-bit count) pairs = 200 KB
-constexpr int PROF_FAST_UNROLL = 8;    // columns in flight per lane (10 warps x 32 lanes x 8 x 8 B = 20 KB per SM)
-constexpr size_t PROF_FAST_SMEM = (size_t)PROF_FAST_NW * PROF_FAST_BINS * 32 * (sizeof(double) + sizeof(unsigned short));
-// points one lane sees in one CTA (its 16-bit counts must hold them): rows per warp x 32-column groups per row
-__host__ __device__ inline long long prof_fast_points_per_lane(int n1, int n2)
-{
-    const long long rows_per_warp = ((long long)FLUSH * n1 + PROF_SUB * PROF_FAST_NW - 1) / (PROF_SUB * PROF_FAST_NW);
-    return rows_per_warp * ((n2 + 31) / 32);
-}
-
-struct ProfFastParams {
-    const double* rho;            // [i_end - i_begin][n1][n2]
-    const double *xx, *yy, *zz;   // squared coordinates as staged for k_energy3d
-    const double* slo;            // [nb + 1] thresholds on s (float32 values on a float32 grid)
-    int n1, n2, i_begin, i_end, nb, dtype;
-    float e0, inv_width;          // first edge and nb / (e[nb] - e[0]): first guess of the bin from a float32 sqrt
-    double* part_sum;             // [flush block][PROF_SUB][nb]
-    long long* part_cnt;
-};
-
-static __global__ void __launch_bounds__(PROF_FAST_NW * 32) k_radial_hist_fast(const ProfFastParams P)
-{
-    extern __shared__ double h_sum[];                       // [PROF_FAST_NW][PROF_FAST_BINS][32], then the counts
-    __shared__ double s_slo[PROF_FAST_BINS + 1];
-    __shared__ double s_wsum[PROF_FAST_NW][PROF_FAST_BINS];
-    __shared__ int s_wcnt[PROF_FAST_NW][PROF_FAST_BINS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nb = P.nb;
-    for (int q = threadIdx.x; q <= nb; q += blockDim.x) s_slo[q] = P.slo[q];
-    double* const mine = h_sum + (size_t)warp * PROF_FAST_BINS * 32 + lane;        // bin b at mine[b * 32]
-    unsigned short* const h_cnt = (unsigned short*)(h_sum + (size_t)PROF_FAST_NW * PROF_FAST_BINS * 32);
-    unsigned short* const mine_c = h_cnt + (size_t)warp * PROF_FAST_BINS * 32 + lane;
-    for (int b = 0; b < nb; ++b) { mine[b * 32] = 0.0; mine_c[b * 32] = 0; }
-    __syncthreads();
-
-    const int sub = blockIdx.x;
-    const int fb = P.i_begin / FLUSH + blockIdx.y;
-    const int ia = fb * FLUSH, ib = min(ia + FLUSH, P.i_end);
-    const int nrows = (ib - ia) * P.n1;
-    const bool f64 = (P.dtype == IWB_F64);
-    for (int row = sub * PROF_FAST_NW + warp; row < nrows; row += PROF_SUB * PROF_FAST_NW) {
-        const int i = ia + row / P.n1, j = row - (row / P.n1) * P.n1;
-        const double* src = P.rho + ((size_t)(i - P.i_begin) * P.n1 + j) * P.n2;
-        const double sxy = P.xx[i] + P.yy[j];
-        const float sxy_f = __fadd_rn((float)P.xx[i], (float)P.yy[j]);
-        for (int k0 = 0; k0 < P.n2; k0 += 32 * PROF_FAST_UNROLL) {
-            double v[PROF_FAST_UNROLL], zz[PROF_FAST_UNROLL];
-#pragma unroll
-            for (int u = 0; u < PROF_FAST_UNROLL; ++u) {             // all loads of the group first
-                const int k = k0 + u * 32 + lane;
-                const bool valid = k < P.n2;
-                v[u] = valid ? __ldcs(src + k) : 0.0;                // streamed: the field is read exactly once
-                zz[u] = valid ? P.zz[k] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < PROF_FAST_UNROLL; ++u) {
-                const int k = k0 + u * 32 + lane;
-                // the evaluator's own s (reproduce_rodal_exact.py:179, 218: float32 arithmetic on a float32 grid)
-                const double s = f64 ? sxy + zz[u] : (double)__fadd_rn(sxy_f, (float)zz[u]);
-                int kb = max(0, min((int)((sqrtf((float)s) - P.e0) * P.inv_width), nb - 1));
-                while (kb > 0 && s < s_slo[kb]) --kb;
-                while (kb < nb && s >= s_slo[kb + 1]) ++kb;          // kb == nb: on or beyond the last edge, in no bin
-                if (k < P.n2 && kb < nb && s >= s_slo[0]) {
-                    mine[kb * 32] += v[u];
-                    mine_c[kb * 32] += 1;
-                }
-            }
-        }
-    }
-    __syncwarp();
-    // lanes -> warp (fixed tree for the sums), then warps in index order
-    for (int b = 0; b < nb; ++b) {
-        double t = mine[b * 32];
-        int c = mine_c[b * 32];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            t += __shfl_xor_sync(0xffffffffu, t, off);
-            c += __shfl_xor_sync(0xffffffffu, c, off);
-        }
-        if (lane == 0) { s_wsum[warp][b] = t; s_wcnt[warp][b] = c; }
-    }
-    __syncthreads();
-    for (int q = threadIdx.x; q < nb; q += blockDim.x) {
-        double a = s_wsum[0][q];
-        long long c = s_wcnt[0][q];
-        for (int w = 1; w < PROF_FAST_NW; ++w) { a += s_wsum[w][q]; c += s_wcnt[w][q]; }
-        const size_t o = ((size_t)fb * PROF_SUB + sub) * nb + q;
-        P.part_sum[o] = a;
-        P.part_cnt[o] = c;
-    }
-}
-
-// ---- run-length flavour (n_bins <= PROF_FAST_BINS): the default ---------------------------------------------------------
-// The lane-private kernel above is latency-bound (200 KB of bins leave 10 warps per SM; ncu: issue slots 27 % busy, a chain
-// of dependent shared-memory read-modify-writes per lane; 1.19 ms per GiB = 0.9 TB/s).  Here a lane walks a CONTIGUOUS
-// chunk of the row (columns [l * c, (l + 1) * c)), where r changes by at most dz per step, so its bin changes about once in
-// bin_width / dz points: the lane keeps the current bin, that bin's two thresholds and the running (sum, count) in
-// registers and touches nothing else until the bin changes.  Then the finished run is handed to the warp's histogram --
-// 64 x 12 bytes of shared memory per warp, so an SM holds 64 warps -- in a fixed order: points in walking order, lanes in
-// ascending order within a step, and the runs still open at the end of the CTA's rows in lane order.  Same bits on every
-// run; warps / CTAs / flush blocks are added in index order as before.
-constexpr int PROF_RLE_NW = 8;
-
-static __global__ void __launch_bounds__(PROF_RLE_NW * 32) k_radial_hist_rle(const ProfFastParams P)
-{
-    __shared__ double s_slo[PROF_FAST_BINS + 2];
-    __shared__ double s_sum[PROF_RLE_NW][PROF_FAST_BINS];
-    __shared__ int s_cnt[PROF_RLE_NW][PROF_FAST_BINS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nb = P.nb;
-    for (int q = threadIdx.x; q <= nb; q += blockDim.x) s_slo[q] = P.slo[q];
-    for (int q = lane; q < PROF_FAST_BINS; q += 32) { s_sum[warp][q] = 0.0; s_cnt[warp][q] = 0; }
-    __syncthreads();
-
-    const int sub = blockIdx.x;
-    const int fb = P.i_begin / FLUSH + blockIdx.y;
-    const int ia = fb * FLUSH, ib = min(ia + FLUSH, P.i_end);
-    const int nrows = (ib - ia) * P.n1;
-    const bool f64 = (P.dtype == IWB_F64);
-    const int chunk = (P.n2 + 31) / 32;
-    const int c0 = lane * chunk, c1 = min(c0 + chunk, P.n2);
-
-    // the open run of this lane: bin cur (-1: none; nb: "in no bin"), its thresholds lo <= s < hi, and what it holds
-    int cur = -1, run_cnt = 0;
-    double lo = 0.0, hi = -1.0, run_sum = 0.0;
-    // hand the runs of the lanes in `mask` to the warp's histogram, lowest lane first (fixed order)
-    auto hand_over = [&](unsigned mask, int b_out, double v_out, int c_out) {
-        while (mask) {
-            const int src = __ffs(mask) - 1;
-            const int b = __shfl_sync(0xffffffffu, b_out, src);
-            const double v = __shfl_sync(0xffffffffu, v_out, src);
-            const int c = __shfl_sync(0xffffffffu, c_out, src);
-            if (lane == 0) { s_sum[warp][b] += v; s_cnt[warp][b] += c; }
-            mask &= mask - 1;
-        }
-    };
-    for (int row = sub * PROF_RLE_NW + warp; row < nrows; row += PROF_SUB * PROF_RLE_NW) {
-        const int i = ia + row / P.n1, j = row - (row / P.n1) * P.n1;
-        const double* src = P.rho + ((size_t)(i - P.i_begin) * P.n1 + j) * P.n2;
-        const double sxy = P.xx[i] + P.yy[j];
-        const float sxy_f = __fadd_rn((float)P.xx[i], (float)P.yy[j]);
-        for (int u = 0; u < chunk; ++u) {                        // warp-uniform trip count
-            const int k = c0 + u;
-            const bool valid = k < c1;
-            double v = 0.0, s = 0.0;
-            if (valid) {
-                v = src[k];                                      // 32-byte sectors are shared by four consecutive steps (L1)
-                const double zz = P.zz[k];
-                s = f64 ? sxy + zz : (double)__fadd_rn(sxy_f, (float)zz);
-            }
-            const bool same = valid && s >= lo && s < hi;        // still inside the open run's bin
-            int b_out = 0, c_out = 0;
-            double v_out = 0.0;
-            if (valid && !same) {
-                // close the open run, find the bin of s against the thresholds (exactly the reference's masks), open a new one
-                b_out = cur; v_out = run_sum; c_out = run_cnt;
-                int kb = (cur < 0) ? 0 : min(cur, nb - 1);
-                while (kb > 0 && s < s_slo[kb]) --kb;
-                while (kb < nb && s >= s_slo[kb + 1]) ++kb;
-                if (s < s_slo[0]) { cur = nb; lo = -INFINITY; hi = s_slo[0]; }            // below the first edge: in no bin
-                else if (kb >= nb) { cur = nb; lo = s_slo[nb]; hi = INFINITY; }             // on / beyond the last edge
-                else { cur = kb; lo = s_slo[kb]; hi = s_slo[kb + 1]; }
-                run_sum = 0.0; run_cnt = 0;
-            }
-            if (valid) { run_sum += v; ++run_cnt; }
-            const unsigned mask = __ballot_sync(0xffffffffu, valid && !same && c_out > 0 && b_out >= 0 && b_out < nb);
-            if (mask) hand_over(mask, b_out, v_out, c_out);
-        }
-    }
-    hand_over(__ballot_sync(0xffffffffu, run_cnt > 0 && cur >= 0 && cur < nb), cur, run_sum, run_cnt);
-    __syncthreads();
-    for (int q = threadIdx.x; q < nb; q += blockDim.x) {
-        double a = s_sum[0][q];
-        long long c = s_cnt[0][q];
-        for (int w = 1; w < PROF_RLE_NW; ++w) { a += s_sum[w][q]; c += s_cnt[w][q]; }
         const size_t o = ((size_t)fb * PROF_SUB + sub) * nb + q;
         P.part_sum[o] = a;
         P.part_cnt[o] = c;
