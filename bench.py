@@ -317,10 +317,59 @@ def run_sweep_opt(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config 2: reproduce_rodal_exact --mode axisym, nx = 2400, ny = 1200, one B200
+# ---------------------------------------------------------------------------------------------------------------------
+def run_axisym(args):
+    """`--config axisym`: one step = one backend.compute_energy_axisymmetric call (host linspace coordinates in, Python
+    floats out), wall clock; the kernel's CUDA-event time beside it; parity against the reference's frozen result."""
+    from irrotational_warp_lab_b200 import backend
+    nx, ny = 2400, 1200
+    kw = dict(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, nx=nx, ny=ny)
+    warmup, steps = max(args.warmup, 3), max(args.steps, 1)
+    for _ in range(warmup):
+        run = backend.compute_energy_axisymmetric(**kw)
+    kms = []
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run = backend.compute_energy_axisymmetric(**kw)
+        kms.append(run["engine"]["kernel_ms"])
+    dt = (time.perf_counter() - t0) / steps
+    with open(os.path.join(ROOT, "tests", "golden", "golden_axisym.json")) as f:
+        gold = json.load(f)["cases"]["axi_2400x1200"]
+    rel = lambda a, b: abs(a - b) / max(abs(b), 1e-300)      # noqa: E731
+    e_at_r = run["_e_at_r"]
+    shell_err = max(max(rel(e_at_r(s["r"])[0], s["e_pos"]), rel(e_at_r(s["r"])[1], s["e_neg"])) for s in gold["shells"])
+    parity = {"against": "tests/golden/golden_axisym.json:axi_2400x1200 (reference)",
+              "e_pos_rel_err": rel(run["energies"]["e_pos"], gold["energies"]["e_pos"]),
+              "e_neg_rel_err": rel(run["energies"]["e_neg"], gold["energies"]["e_neg"]),
+              "shell_rel_err": shell_err,
+              "counts_exact": (run["counts"]["pos"], run["counts"]["neg"], run["counts"]["zero"]) ==
+                              (gold["cnt_pos"], gold["cnt_neg"], gold["cnt_zero"])}
+    assert parity["counts_exact"] and max(parity["e_pos_rel_err"], parity["e_neg_rel_err"], shell_err) < 1e-10, parity
+    from oracle import oracle_np
+    t1 = time.perf_counter()
+    oracle_np.energy_axisym(shells=SHELLS, **kw)
+    t_cpu = time.perf_counter() - t1
+    pts = nx * ny
+    print(json.dumps({
+        "metric": "axisym Gpoints/s (fp64, nx=2400 ny=1200)", "value": pts / dt / 1e9, "unit": "Gpoints/s", "n_gpus": 1,
+        "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "none",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2: compute_energy_axisymmetric rho=5 sigma=4 v=1 extent=66 nx=2400 ny=1200, "
+                               "shells r<=40 and r<=60, through the public API (host buffers in, Python floats out)"},
+        "kernel_ms": statistics.median(kms), "kernel_gpoints_per_s": pts / (statistics.median(kms) * 1e-3) / 1e9,
+        "parity": parity,
+        "cpu_baseline": {"value": pts / t_cpu / 1e9, "unit": "Gpoints/s", "cores": 1, "kind": "port",
+                         "sample": "one evaluation of the NumPy port at the same size (the reference is single-threaded)"},
+    }))
+    return 0
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", choices=["headline", "sweep_opt"], default="headline",
-                    help="headline: BASELINE config 4 (the driver's line); sweep_opt: BASELINE config 5")
+    ap.add_argument("--config", choices=["headline", "sweep_opt", "axisym"], default="headline",
+                    help="headline: BASELINE config 4 (the driver's line); sweep_opt: BASELINE config 5; axisym: config 2")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -334,6 +383,8 @@ def main(argv=None):
         return run_reference(args)
     if args.config == "sweep_opt":
         return run_sweep_opt(args)
+    if args.config == "axisym":
+        return run_axisym(args)
 
     import torch
     import torch.distributed as dist

@@ -63,13 +63,14 @@ struct Launch3 {
     K3Params P;
     int dtype, mode, nshell, cfg_id, ntiles, fb0, fb1;
     int tile_stride, tile_first;       // tile_stride > 1: interleaved tile shard (chain sums instead of table rows)
+    int ctas;                          // persistent CTAs of the launch (the span table was made for this many)
     bool emit;
 };
 
 // One cached host preparation (see prepare_host) and the handle's small LRU set of them.
 struct PrepEntry {
     bool valid = false, emit = false;
-    int static_pct = -1, cfg = 0;
+    int static_pct = -1, cfg = 0, ctas = 0;
     unsigned long long stamp = 0;
     iwb_params3d key;                  // scalars only (pointers nulled)
     std::vector<double> coords;        // x | y | z as given
@@ -132,11 +133,13 @@ static int prepare_host(iwb_handle* h, const iwb_params3d* p, bool emit, PrepEnt
     // tiles and finishes 3 % late, and a multi-GPU step waits for the slowest rank; profiles/r2_shard_static_sweep.log)
     const int static_pct = h->k3_static_pct >= 0 ? h->k3_static_pct
                            : ((p->i_begin == 0 && p->i_end == n0) ? (tstride >= 8 ? 60 : 80) : 70);
+    // persistent CTAs: one per SM, or the share of the SMs a batch gives each of its concurrent evaluations (k3_ctas)
+    const int ctas = (h->k3_ctas > 0 && h->k3_ctas < h->sm_count) ? h->k3_ctas : h->sm_count;
     const std::vector<int> spans = make_spans((long long)(ntiles_local > 0 ? ntiles_local : 0) *
                                                   ((p->i_end - p->i_begin + FLUSH - 1) / FLUSH),
-                                              h->sm_count, static_pct);
+                                              ctas, static_pct);
     // coordinates: x, x*x, y*y, z*z (squares rounded once in the coordinate dtype, as x*x is in NumPy)
-    const size_t ncoord = (size_t)2 * n0 + n1 + n2;
+    const size_t ncoord = (size_t)2 * n0 + n1 + n2 + (IWB_XLATE ? (size_t)2 * n0 : 0);   // + {x, x*x} pairs (IWB_XLATE)
     E.ncoord = ncoord;
     E.stage.assign((ncoord * sizeof(double) + spans.size() * sizeof(int) + 7) / 8, 0.0);
     double* hc = E.stage.data();
@@ -150,6 +153,9 @@ static int prepare_host(iwb_handle* h, const iwb_params3d* p, bool emit, PrepEnt
         for (int j = 0; j < n1; ++j) { float f = (float)p->y[j]; hyy[j] = (double)(f * f); }
         for (int k = 0; k < n2; ++k) { float f = (float)p->z[k]; hzz[k] = (double)(f * f); }
     }
+#if IWB_XLATE
+    for (int i = 0; i < n0; ++i) { hzz[n2 + 2 * i] = hx[i]; hzz[n2 + 2 * i + 1] = hxx[i]; }
+#endif
     memcpy(hc + ncoord, spans.data(), spans.size() * sizeof(int));
     E.stage_bytes = ncoord * sizeof(double) + spans.size() * sizeof(int);
 
@@ -188,7 +194,7 @@ static int prepare_host(iwb_handle* h, const iwb_params3d* p, bool emit, PrepEnt
     }
     P.shell_thr_max = -1.0;
     for (int s = 0; s < p->nshell; ++s) P.shell_thr_max = fmax(P.shell_thr_max, P.shell_thr[s]);
-    L->dtype = p->dtype; L->mode = p->mode; L->nshell = p->nshell; L->cfg_id = cfg_id; L->ntiles = ntiles; L->emit = emit;
+    L->dtype = p->dtype; L->mode = p->mode; L->nshell = p->nshell; L->cfg_id = cfg_id; L->ntiles = ntiles; L->emit = emit; L->ctas = ctas;
     L->fb0 = p->i_begin / FLUSH; L->fb1 = (p->i_end + FLUSH - 1) / FLUSH;
     L->tile_stride = tstride; L->tile_first = tfirst;
     return IWB_OK;
@@ -202,7 +208,7 @@ static int prepared(iwb_handle* h, const iwb_params3d* p, bool emit, const PrepE
     PrepCache& C = *(PrepCache*)h->prep;
     auto same = [&](const PrepEntry& E) {
         const iwb_params3d& q = E.key;
-        if (!(E.valid && E.emit == emit && E.static_pct == h->k3_static_pct && E.cfg == h->k3_config)) return false;
+        if (!(E.valid && E.emit == emit && E.static_pct == h->k3_static_pct && E.cfg == h->k3_config && E.ctas == h->k3_ctas)) return false;
         if (!(q.dtype == p->dtype && q.mode == p->mode && q.n0 == p->n0 && q.n1 == p->n1 && q.n2 == p->n2 &&
               q.i_begin == p->i_begin && q.i_end == p->i_end && q.nshell == p->nshell &&
               q.tile_stride == p->tile_stride && q.tile_first == p->tile_first)) return false;
@@ -228,7 +234,7 @@ static int prepared(iwb_handle* h, const iwb_params3d* p, bool emit, const PrepE
     memcpy(E.coords.data(), p->x, sizeof(double) * p->n0);
     memcpy(E.coords.data() + p->n0, p->y, sizeof(double) * p->n1);
     memcpy(E.coords.data() + p->n0 + p->n1, p->z, sizeof(double) * p->n2);
-    E.emit = emit; E.static_pct = h->k3_static_pct; E.cfg = h->k3_config;
+    E.emit = emit; E.static_pct = h->k3_static_pct; E.cfg = h->k3_config; E.ctas = h->k3_ctas;
     E.valid = true; E.stamp = ++C.clock;
     *out = &E;
     return IWB_OK;
@@ -252,6 +258,9 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
     const int n0 = p->n0, n1 = p->n1;
     P.span_begin = (const int*)(dc + E->ncoord);
     P.x = dc; P.xx = dc + n0; P.yy = dc + 2 * n0; P.zz = dc + 2 * n0 + n1;
+#if IWB_XLATE
+    P.xq = (const double2*)(dc + 2 * n0 + n1 + p->n2);
+#endif
     const int nfb_total = (n0 + FLUSH - 1) / FLUSH;
     IWB_CUDA(partial.reserve((size_t)nfb_total * L->ntiles * ROW * sizeof(double)));
     P.partial = (double*)partial.p;
@@ -270,7 +279,7 @@ static int launch_slab(iwb_handle* h, const Launch3& L, double* table, cudaStrea
 {
     static_assert(IWB_TILE_CHAINS == 16, "k_reduce_tiles is launched with 16 chains");
     if (L.P.nspans > 0) {
-        cudaError_t e = launch_k3(L.dtype, L.mode, L.nshell, L.emit, L.cfg_id, L.P, h->sm_count, st);
+        cudaError_t e = launch_k3(L.dtype, L.mode, L.nshell, L.emit, L.cfg_id, L.P, L.ctas, st);
         if (e != cudaSuccess) return fail(IWB_ERR_CUDA, std::string("k_energy3d launch: ") + cudaGetErrorString(e));
     }
     if (tiles_out)
@@ -653,7 +662,7 @@ static int launch_exchange(iwb_handle* h, iwb_peer* pr, const Launch3& L, int nf
 {
     const int S = pr->world, first = pr->rank;
     if (L.P.nspans > 0) {
-        cudaError_t e = launch_k3(L.dtype, L.mode, L.nshell, L.emit, L.cfg_id, L.P, h->sm_count, st);
+        cudaError_t e = launch_k3(L.dtype, L.mode, L.nshell, L.emit, L.cfg_id, L.P, L.ctas, st);
         if (e != cudaSuccess) return fail(IWB_ERR_CUDA, std::string("k_energy3d launch: ") + cudaGetErrorString(e));
     }
     const unsigned long long epoch = ++pr->epoch;
@@ -880,25 +889,49 @@ int iwb_energy3d_batch(iwb_handle* h, int npoints, const iwb_params3d* pts, iwb_
     }
     auto t0 = std::chrono::steady_clock::now();
     IWB_CUDA(cudaSetDevice(h->device));
-    // NSCRATCH evaluations in flight; a scratch is recycled after its previous occupant completed
-    for (int base = 0; base < npoints; base += NSCRATCH) {
-        const int m = (npoints - base < NSCRATCH) ? npoints - base : NSCRATCH;
-        for (int q = 0; q < m; ++q) {
-            int rc = enqueue_full(h, h->scr[q], &pts[base + q]);
-            if (rc) return rc;
+    // Small grids: an evaluation of n = 256 is 640 work units, 4.3 per CTA of a full-width launch -- every span pays its
+    // phi prologue and the dynamic tail is single units.  A batch therefore gives each of its NSCRATCH concurrent
+    // evaluations a share of the SMs (their CTAs each need a whole SM's shared memory, so the launches tile the GPU):
+    // four times the units per CTA, a quarter of the prologues, and the tail of one launch overlaps the others.  The
+    // result does not depend on the number of CTAs (fixed result slots).  Large grids keep the full width.
+    const int saved_ctas = h->k3_ctas;
+    const int conc = npoints < NSCRATCH ? npoints : NSCRATCH;
+    if (h->batch_split && conc > 1) {
+        long long units_max = 0;
+        for (int q = 0; q < npoints; ++q) {
+            const K3Config cfg = kConfigs[config_is_built(h->k3_config, pts[q].dtype, pts[q].nshell, false) ? h->k3_config : 0];
+            const long long u = (long long)tiles_j(pts[q].n1, cfg.rj) * tiles_k(pts[q].n2) *
+                                ((pts[q].i_end - pts[q].i_begin + FLUSH - 1) / FLUSH);
+            if (u > units_max) units_max = u;
         }
-        for (int q = 0; q < m; ++q) {
-            Scratch& c = h->scr[q];
-            IWB_CUDA(cudaStreamSynchronize(c.stream));
-            memset(&outs[base + q], 0, sizeof(iwb_result));
-            unpack_row((const double*)c.h_out.p, pts[base + q].nshell, &outs[base + q]);
-            outs[base + q].cnt_nan = (int64_t)(pts[base + q].i_end - pts[base + q].i_begin) * pts[base + q].n1 * pts[base + q].n2 -
-                                     outs[base + q].cnt_pos - outs[base + q].cnt_neg - outs[base + q].cnt_zero;
-            apply_reference_nonfinite(&outs[base + q], pts[base + q].nshell);
-            float ms = 0;
-            IWB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
-            outs[base + q].kernel_ms = ms;
-        }
+        const int parts = h->batch_split == 1 ? conc : (h->batch_split < conc ? h->batch_split : conc);
+        if (units_max < 24LL * h->sm_count && parts > 1) h->k3_ctas = h->sm_count / parts;
+    }
+    // rolling pipeline: slot q is re-armed with the next point as soon as its previous occupant has been read back
+    auto collect = [&](int slot, int idx) -> int {
+        Scratch& c = h->scr[slot];
+        IWB_CUDA(cudaStreamSynchronize(c.stream));
+        memset(&outs[idx], 0, sizeof(iwb_result));
+        unpack_row((const double*)c.h_out.p, pts[idx].nshell, &outs[idx]);
+        outs[idx].cnt_nan = (int64_t)(pts[idx].i_end - pts[idx].i_begin) * pts[idx].n1 * pts[idx].n2 -
+                            outs[idx].cnt_pos - outs[idx].cnt_neg - outs[idx].cnt_zero;
+        apply_reference_nonfinite(&outs[idx], pts[idx].nshell);
+        float ms = 0;
+        IWB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+        outs[idx].kernel_ms = ms;
+        return IWB_OK;
+    };
+    int rc = IWB_OK;
+    for (int q = 0; q < npoints && rc == IWB_OK; ++q) {
+        const int slot = q % NSCRATCH;
+        if (q >= NSCRATCH) rc = collect(slot, q - NSCRATCH);
+        if (rc == IWB_OK) rc = enqueue_full(h, h->scr[slot], &pts[q]);
+    }
+    for (int q = (npoints > NSCRATCH ? npoints - NSCRATCH : 0); q < npoints && rc == IWB_OK; ++q) rc = collect(q % NSCRATCH, q);
+    h->k3_ctas = saved_ctas;
+    if (rc) {
+        for (int s2 = 0; s2 < NSCRATCH; ++s2) cudaStreamSynchronize(h->scr[s2].stream);    // leave no launch behind
+        return rc;
     }
     const double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     for (int q = 0; q < npoints; ++q) outs[q].total_ms = total;

@@ -42,7 +42,7 @@ struct AxParams {
 constexpr int AX_RJ = 32, AX_NW = 8, AX_NB = AX_RJ / AX_NW, AX_PLANE = AX_RJ * RK;
 
 template <int DT, int NSH, bool EMIT>
-__global__ void __launch_bounds__(AX_NW * 32) k_axisym(const __grid_constant__ AxParams P)
+__global__ void __launch_bounds__(AX_NW * 32, 3) k_axisym(const __grid_constant__ AxParams P)
 {
     __shared__ double ph[AX_PLANE];
     __shared__ double px[AX_PLANE];
@@ -78,20 +78,31 @@ __global__ void __launch_bounds__(AX_NW * 32) k_axisym(const __grid_constant__ A
     }
 
     // ---- phase 1: phi on the region (z = 0: r = sqrt((x*x + y*y) + 0)) ---------------------------
+    // The NB rows of one column share x: NB independent evaluations per call, so their sqrt / division chains overlap.
+    // The host's operand-range proof (phi_fast_path_is_safe, as for the 3D evaluator) covers every point but the origin
+    // r == 0; the thread that holds it, and every thread of an exotic grid, takes the reference flavour.  (Measured on
+    // B200, 2400 x 1200 / 4800 x 2400, event time with the tile reduction: one point at a time with per-point range tests
+    // 0.079 / 0.270 ms; grouped with per-point range tests 0.114 / 0.405 ms; grouped + host proof + seeded divisions
+    // 0.074 / 0.249 ms; the same with three CTAs per SM 0.067 / 0.223 ms -- profiles/r2_ab17_axisym.log.)
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
+    for (int a = 0; a < 2; ++a) {
+        double f[NB];
+        bool force_ref = !P.pc.prechecked;
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            double f[1];
-            if (DT == IWB_F64) {
-                double s[1] = {xxv[a] + yyv[b]};
-                phi_exact_f64<1, false>(s, xv[a], P.pc, f);
-            } else {
-                float s[1] = {__fadd_rn((float)xxv[a], (float)yyv[b])};
-                phi_exact_f32ref<1, false>(s, (float)xv[a], P.pc, f);
-            }
-            ph[jr_[b] * RK + tx + 32 * a] = f[0];
+        for (int b = 0; b < NB; ++b) force_ref = force_ref || (xxv[a] == 0.0 && yyv[b] == 0.0);
+        if (DT == IWB_F64) {
+            double s[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) s[b] = xxv[a] + yyv[b];
+            phi_exact_f64<NB, true>(s, xv[a], P.pc, f, force_ref);
+        } else {
+            float s[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) s[b] = __fadd_rn((float)xxv[a], (float)yyv[b]);
+            phi_exact_f32ref<NB, true>(s, (float)xv[a], P.pc, f, force_ref);
         }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) ph[jr_[b] * RK + tx + 32 * a] = f[b];
     }
     __syncthreads();
 
@@ -369,6 +380,14 @@ int iwb_energy_axisym(iwb_handle* h, const iwb_params_axisym* p, iwb_result* out
     double* dc = (double*)c.coords.p;
     P.x = dc; P.xx = dc + nx; P.y = dc + 2 * nx; P.yy = P.y + ny; P.dV = P.yy + ny;
     P.pc = make_phi_const(p->rho, p->sigma, p->v, p->eps, p->sinh_rs, p->cosh_rs);
+    {   // operand ranges of the branch-free phi on this half-plane (z == 0), as for the 3D evaluator
+        const double zero = 0.0;
+        const double* const coords[3] = {p->x, p->y, &zero};
+        const int nn[3] = {nx, ny, 1};
+        int zero_index[3];
+        P.pc.prechecked = phi_fast_path_is_safe(coords, nn, p->rho, p->sigma, p->v, p->eps, p->sinh_rs, p->cosh_rs,
+                                                zero_index, p->dtype != IWB_F64) ? 1 : 0;
+    }
     P.cx = make_axis_coef(p->dx); P.cy = make_axis_coef(p->dy);
     P.c16pi = 16.0 * 3.141592653589793; P.rc16pi = 1.0 / P.c16pi;
     for (int s = 0; s < IWB_MAX_SHELLS; ++s)
