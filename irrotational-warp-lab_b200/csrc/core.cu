@@ -252,8 +252,6 @@ int iwb_create(int device_id, iwb_handle** out)
     const char* sp = getenv("IWB_K3_STATIC_PCT");
     h->k3_static_pct = sp ? atoi(sp) : -1;
     if (h->k3_static_pct < -1 || h->k3_static_pct > 100) h->k3_static_pct = -1;
-    const char* bs = getenv("IWB_BATCH_SPLIT");
-    h->batch_split = bs ? atoi(bs) : 1;
     *out = h;
     return IWB_OK;
 }

@@ -63,14 +63,13 @@ struct Launch3 {
     K3Params P;
     int dtype, mode, nshell, cfg_id, ntiles, fb0, fb1;
     int tile_stride, tile_first;       // tile_stride > 1: interleaved tile shard (chain sums instead of table rows)
-    int ctas;                          // persistent CTAs of the launch (the span table was made for this many)
     bool emit;
 };
 
 // One cached host preparation (see prepare_host) and the handle's small LRU set of them.
 struct PrepEntry {
     bool valid = false, emit = false;
-    int static_pct = -1, cfg = 0, ctas = 0;
+    int static_pct = -1, cfg = 0;
     unsigned long long stamp = 0;
     iwb_params3d key;                  // scalars only (pointers nulled)
     std::vector<double> coords;        // x | y | z as given
@@ -133,13 +132,11 @@ static int prepare_host(iwb_handle* h, const iwb_params3d* p, bool emit, PrepEnt
     // tiles and finishes 3 % late, and a multi-GPU step waits for the slowest rank; profiles/r2_shard_static_sweep.log)
     const int static_pct = h->k3_static_pct >= 0 ? h->k3_static_pct
                            : ((p->i_begin == 0 && p->i_end == n0) ? (tstride >= 8 ? 60 : 80) : 70);
-    // persistent CTAs: one per SM, or the share of the SMs a batch gives each of its concurrent evaluations (k3_ctas)
-    const int ctas = (h->k3_ctas > 0 && h->k3_ctas < h->sm_count) ? h->k3_ctas : h->sm_count;
     const std::vector<int> spans = make_spans((long long)(ntiles_local > 0 ? ntiles_local : 0) *
                                                   ((p->i_end - p->i_begin + FLUSH - 1) / FLUSH),
-                                              ctas, static_pct);
+                                              h->sm_count, static_pct);
     // coordinates: x, x*x, y*y, z*z (squares rounded once in the coordinate dtype, as x*x is in NumPy)
-    const size_t ncoord = (size_t)2 * n0 + n1 + n2 + (IWB_XLATE ? (size_t)2 * n0 : 0);   // + {x, x*x} pairs (IWB_XLATE)
+    const size_t ncoord = (size_t)2 * n0 + n1 + n2;
     E.ncoord = ncoord;
     E.stage.assign((ncoord * sizeof(double) + spans.size() * sizeof(int) + 7) / 8, 0.0);
     double* hc = E.stage.data();
@@ -153,9 +150,6 @@ static int prepare_host(iwb_handle* h, const iwb_params3d* p, bool emit, PrepEnt
         for (int j = 0; j < n1; ++j) { float f = (float)p->y[j]; hyy[j] = (double)(f * f); }
         for (int k = 0; k < n2; ++k) { float f = (float)p->z[k]; hzz[k] = (double)(f * f); }
     }
-#if IWB_XLATE
-    for (int i = 0; i < n0; ++i) { hzz[n2 + 2 * i] = hx[i]; hzz[n2 + 2 * i + 1] = hxx[i]; }
-#endif
     memcpy(hc + ncoord, spans.data(), spans.size() * sizeof(int));
     E.stage_bytes = ncoord * sizeof(double) + spans.size() * sizeof(int);
 
@@ -194,7 +188,7 @@ static int prepare_host(iwb_handle* h, const iwb_params3d* p, bool emit, PrepEnt
     }
     P.shell_thr_max = -1.0;
     for (int s = 0; s < p->nshell; ++s) P.shell_thr_max = fmax(P.shell_thr_max, P.shell_thr[s]);
-    L->dtype = p->dtype; L->mode = p->mode; L->nshell = p->nshell; L->cfg_id = cfg_id; L->ntiles = ntiles; L->emit = emit; L->ctas = ctas;
+    L->dtype = p->dtype; L->mode = p->mode; L->nshell = p->nshell; L->cfg_id = cfg_id; L->ntiles = ntiles; L->emit = emit;
     L->fb0 = p->i_begin / FLUSH; L->fb1 = (p->i_end + FLUSH - 1) / FLUSH;
     L->tile_stride = tstride; L->tile_first = tfirst;
     return IWB_OK;
@@ -208,7 +202,7 @@ static int prepared(iwb_handle* h, const iwb_params3d* p, bool emit, const PrepE
     PrepCache& C = *(PrepCache*)h->prep;
     auto same = [&](const PrepEntry& E) {
         const iwb_params3d& q = E.key;
-        if (!(E.valid && E.emit == emit && E.static_pct == h->k3_static_pct && E.cfg == h->k3_config && E.ctas == h->k3_ctas)) return false;
+        if (!(E.valid && E.emit == emit && E.static_pct == h->k3_static_pct && E.cfg == h->k3_config)) return false;
         if (!(q.dtype == p->dtype && q.mode == p->mode && q.n0 == p->n0 && q.n1 == p->n1 && q.n2 == p->n2 &&
               q.i_begin == p->i_begin && q.i_end == p->i_end && q.nshell == p->nshell &&
               q.tile_stride == p->tile_stride && q.tile_first == p->tile_first)) return false;
@@ -234,7 +228,7 @@ static int prepared(iwb_handle* h, const iwb_params3d* p, bool emit, const PrepE
     memcpy(E.coords.data(), p->x, sizeof(double) * p->n0);
     memcpy(E.coords.data() + p->n0, p->y, sizeof(double) * p->n1);
     memcpy(E.coords.data() + p->n0 + p->n1, p->z, sizeof(double) * p->n2);
-    E.emit = emit; E.static_pct = h->k3_static_pct; E.cfg = h->k3_config; E.ctas = h->k3_ctas;
+    E.emit = emit; E.static_pct = h->k3_static_pct; E.cfg = h->k3_config;
     E.valid = true; E.stamp = ++C.clock;
     *out = &E;
     return IWB_OK;
@@ -258,9 +252,6 @@ static int prepare_slab(iwb_handle* h, const iwb_params3d* p, PinBuf& h_coords, 
     const int n0 = p->n0, n1 = p->n1;
     P.span_begin = (const int*)(dc + E->ncoord);
     P.x = dc; P.xx = dc + n0; P.yy = dc + 2 * n0; P.zz = dc + 2 * n0 + n1;
-#if IWB_XLATE
-    P.xq = (const double2*)(dc + 2 * n0 + n1 + p->n2);
-#endif
     const int nfb_total = (n0 + FLUSH - 1) / FLUSH;
     IWB_CUDA(partial.reserve((size_t)nfb_total * L->ntiles * ROW * sizeof(double)));
     P.partial = (double*)partial.p;
@@ -279,7 +270,7 @@ static int launch_slab(iwb_handle* h, const Launch3& L, double* table, cudaStrea
 {
     static_assert(IWB_TILE_CHAINS == 16, "k_reduce_tiles is launched with 16 chains");
     if (L.P.nspans > 0) {
-        cudaError_t e = launch_k3(L.dtype, L.mode, L.nshell, L.emit, L.cfg_id, L.P, L.ctas, st);
+        cudaError_t e = launch_k3(L.dtype, L.mode, L.nshell, L.emit, L.cfg_id, L.P, h->sm_count, st);
         if (e != cudaSuccess) return fail(IWB_ERR_CUDA, std::string("k_energy3d launch: ") + cudaGetErrorString(e));
     }
     if (tiles_out)
@@ -662,7 +653,7 @@ static int launch_exchange(iwb_handle* h, iwb_peer* pr, const Launch3& L, int nf
 {
     const int S = pr->world, first = pr->rank;
     if (L.P.nspans > 0) {
-        cudaError_t e = launch_k3(L.dtype, L.mode, L.nshell, L.emit, L.cfg_id, L.P, L.ctas, st);
+        cudaError_t e = launch_k3(L.dtype, L.mode, L.nshell, L.emit, L.cfg_id, L.P, h->sm_count, st);
         if (e != cudaSuccess) return fail(IWB_ERR_CUDA, std::string("k_energy3d launch: ") + cudaGetErrorString(e));
     }
     const unsigned long long epoch = ++pr->epoch;
@@ -889,24 +880,9 @@ int iwb_energy3d_batch(iwb_handle* h, int npoints, const iwb_params3d* pts, iwb_
     }
     auto t0 = std::chrono::steady_clock::now();
     IWB_CUDA(cudaSetDevice(h->device));
-    // Small grids: an evaluation of n = 256 is 640 work units, 4.3 per CTA of a full-width launch -- every span pays its
-    // phi prologue and the dynamic tail is single units.  A batch therefore gives each of its NSCRATCH concurrent
-    // evaluations a share of the SMs (their CTAs each need a whole SM's shared memory, so the launches tile the GPU):
-    // four times the units per CTA, a quarter of the prologues, and the tail of one launch overlaps the others.  The
-    // result does not depend on the number of CTAs (fixed result slots).  Large grids keep the full width.
-    const int saved_ctas = h->k3_ctas;
-    const int conc = npoints < NSCRATCH ? npoints : NSCRATCH;
-    if (h->batch_split && conc > 1) {
-        long long units_max = 0;
-        for (int q = 0; q < npoints; ++q) {
-            const K3Config cfg = kConfigs[config_is_built(h->k3_config, pts[q].dtype, pts[q].nshell, false) ? h->k3_config : 0];
-            const long long u = (long long)tiles_j(pts[q].n1, cfg.rj) * tiles_k(pts[q].n2) *
-                                ((pts[q].i_end - pts[q].i_begin + FLUSH - 1) / FLUSH);
-            if (u > units_max) units_max = u;
-        }
-        const int parts = h->batch_split == 1 ? conc : (h->batch_split < conc ? h->batch_split : conc);
-        if (units_max < 24LL * h->sm_count && parts > 1) h->k3_ctas = h->sm_count / parts;
-    }
+    // (Giving each of the NSCRATCH concurrent evaluations of a batch of small grids its own quarter of the SMs -- four
+    // times the units per CTA, a quarter of the phi prologues -- was measured and lost: 50 x n = 256: 72.5 against 78.5
+    // Gpoints/s, n = 400: 95.1 against 99.3, two halves: no difference; profiles/r2_ab18_batch_split.log.)
     // rolling pipeline: slot q is re-armed with the next point as soon as its previous occupant has been read back
     auto collect = [&](int slot, int idx) -> int {
         Scratch& c = h->scr[slot];
@@ -928,7 +904,6 @@ int iwb_energy3d_batch(iwb_handle* h, int npoints, const iwb_params3d* pts, iwb_
         if (rc == IWB_OK) rc = enqueue_full(h, h->scr[slot], &pts[q]);
     }
     for (int q = (npoints > NSCRATCH ? npoints - NSCRATCH : 0); q < npoints && rc == IWB_OK; ++q) rc = collect(q % NSCRATCH, q);
-    h->k3_ctas = saved_ctas;
     if (rc) {
         for (int s2 = 0; s2 < NSCRATCH; ++s2) cudaStreamSynchronize(h->scr[s2].stream);    // leave no launch behind
         return rc;

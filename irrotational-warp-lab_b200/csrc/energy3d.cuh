@@ -49,9 +49,6 @@
 #ifndef IWB_OC_UNROLL
 #define IWB_OC_UNROLL 1     // both rows of the O + C loop unrolled: no loop overhead, row b's loads overlap row a's tally (+0.9 %)
 #endif
-#ifndef IWB_XLATE
-#define IWB_XLATE 0    // experiment: task P loads its plane's {x, x*x} pair right before it runs instead of in the step head
-#endif
 #ifndef IWB_P4
 #define IWB_P4 1       // task P evaluates both rows of a warp at once: four independent phi evaluations per thread
 #endif
@@ -78,9 +75,6 @@ struct K3Params {
     const double* xx;              // [n0]  x*x   (rounded in the path's coordinate dtype)
     const double* yy;              // [n1]  y*y
     const double* zz;              // [n2]  z*z
-#if IWB_XLATE
-    const double2* xq;             // [n0]  {x, x*x}
-#endif
     PhiConst pc;
     AxisCoef cx, cy, cz;
     double dV;                     // (dx*dy)*dz
@@ -693,11 +687,7 @@ k_energy3d(const __grid_constant__ K3Params P)
             const bool doC = (i + 1 < i1);
             // coordinates of this step's planes, requested before the tasks that hide their latency
             const int pn = min(produced + 1, P.n0 - 1);
-#if IWB_XLATE
-            const double xxi = P.xx[i];
-#else
             const double xp_n = P.x[pn], xxp_n = P.xx[pn], xxi = P.xx[i];
-#endif
             const int m3p1 = (m3 == 2) ? 0 : m3 + 1;
             // What OTHER warps' next step needs from this warp is O(i) (they rewrite the phi_y/phi_z buffer it reads)
             // and C(i+1) (phi_y/phi_z(i+1) for their O(i+1); phi(i+1) dead for their P(i+4)).  Task P touches only ring
@@ -707,11 +697,7 @@ k_energy3d(const __grid_constant__ K3Params P)
             const int pp = produced + 1;
             runOC(i, xxi, doC, m3p1);
             step_arrive();
-#if IWB_XLATE
-            if (doP) { const double2 xq = P.xq[pp]; runP(pp, (pp == i + 3) ? m3 : pp % 3, xq.x, xq.y); }
-#else
             if (doP) runP(pp, (pp == i + 3) ? m3 : pp % 3, xp_n, xxp_n);
-#endif
             if (doL) taskP_last();
             step_wait();
             if (doP) ++produced;

@@ -113,10 +113,6 @@ struct iwb_handle {
     int k3_config = 0;         // kernel geometry variant (IWB_K3_CONFIG env override)
     int k3_static_pct = -1;    // share of the work units handed out as one large span per CTA; -1 = automatic (80 / 70 %),
                                // IWB_K3_STATIC_PCT env override
-    int k3_ctas = 0;           // persistent CTAs per launch of the fused kernel; 0 = one per SM (set by iwb_energy3d_batch
-                               // for the duration of a batch of small grids)
-    int batch_split = 1;       // batches of small grids share the SMs between their concurrent evaluations
-                               // (1: one share per concurrent evaluation; IWB_BATCH_SPLIT=0 switches it off, =N forces N shares: A/B timing)
 };
 
 namespace iwb {
