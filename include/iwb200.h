@@ -285,6 +285,11 @@ int iwb_debug_spans(long long units, int ctas, int static_pct, int *out, int cap
 int iwb_debug_tiles_k(int n, int *out, int cap);
 /* the same for the rows (j) of the default 40-row region: 36 output rows per interior tile, 38 in the tiles at the j faces */
 int iwb_debug_tiles_j(int n, int *out, int cap);
+/* Which path the last iwb_radial_profile3d call on this handle took: 1 = bins accumulated inside the fused kernel,
+ * 2 = rho emitted and binned in a second pass (volumes below 2^29 points, where that is faster; more than 144 bins; more
+ * than two shells; bins narrower than a work unit's window of 14; IWB_PROFILE_FUSED=0), 0 = no call yet.
+ * IWB_PROFILE_FUSED=2 takes the fused kernel whenever it can.  Diagnostic for the tests. */
+int iwb_debug_profile_path(iwb_handle *h);
 
 /* Test hook: the branch-free division / square-root sequences of the exact kernels against the built-in
  * IEEE operators on `count` pseudo-random operand pairs (wide_exponents != 0 also exercises the range

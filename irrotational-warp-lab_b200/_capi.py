@@ -145,6 +145,7 @@ SYMBOLS = {
     "iwb_debug_spans": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "iwb_debug_tiles_k": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int]),
     "iwb_debug_tiles_j": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int]),
+    "iwb_debug_profile_path": (C.c_int, [C.c_void_p]),
     "iwb_selftest_constdiv": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
 }
 

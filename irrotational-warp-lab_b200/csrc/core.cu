@@ -56,6 +56,35 @@ double shell_threshold_f32(double R)
     return (double)s;
 }
 
+// Smallest s >= 0 with RN(sqrt(s)) >= e: the profile's lower-edge test r >= edges[q] (tail.py:75) applied to
+// s = (x*x + y*y) + z*z before the square root (fused radial profile, k_energy3d_prof).
+double profile_threshold_f64(double e)
+{
+    if (!(e > 0.0)) return 0.0;
+    double s = e * e;
+    if (isinf(s)) {
+        s = 1.7976931348623157e308;
+        if (sqrt(s) < e) return INFINITY;
+    }
+    while (s > 0.0 && sqrt(nextafter(s, -INFINITY)) >= e) s = nextafter(s, -INFINITY);
+    while (sqrt(s) < e) s = nextafter(s, INFINITY);
+    return s;
+}
+
+// float32 grid: s and r are float32, the comparison with the (float64) edge is made in float64 (radial_profile.cuh)
+double profile_threshold_f32(double e)
+{
+    if (!(e > 0.0)) return 0.0;
+    float s = (float)(e * e);
+    if (isinf(s)) {
+        s = 3.4028234663852886e38f;
+        if ((double)sqrtf(s) < e) return INFINITY;
+    }
+    while (s > 0.0f && (double)sqrtf(nextafterf(s, -INFINITY)) >= e) s = nextafterf(s, -INFINITY);
+    while ((double)sqrtf(s) < e) s = nextafterf(s, INFINITY);
+    return (double)s;
+}
+
 // true when |v| is +0 or 2^lo <= |v| <= 2^hi
 static bool zero_or_in_range(double v, int lo, int hi)
 {
@@ -252,6 +281,8 @@ int iwb_create(int device_id, iwb_handle** out)
     const char* sp = getenv("IWB_K3_STATIC_PCT");
     h->k3_static_pct = sp ? atoi(sp) : -1;
     if (h->k3_static_pct < -1 || h->k3_static_pct > 100) h->k3_static_pct = -1;
+    const char* pf = getenv("IWB_PROFILE_FUSED");
+    h->profile_fused = pf ? atoi(pf) : 1;
     *out = h;
     return IWB_OK;
 }

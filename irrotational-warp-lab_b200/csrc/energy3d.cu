@@ -543,6 +543,8 @@ int iwb_debug_tiles_k(int n, int* out, int cap)
     return nt;
 }
 
+int iwb_debug_profile_path(iwb_handle* h) { return h ? h->last_profile_path : 0; }
+
 int iwb_debug_tiles_j(int n, int* out, int cap)
 {
     const int rj = kConfigs[1].rj;       // the default geometry (region of 40 rows)
@@ -726,6 +728,85 @@ int iwb_reduce_chains(iwb_handle* h, const double* gathered_device, int tile_str
     return IWB_OK;
 }
 
+}  // extern "C"
+
+// Radial profile inside the fused kernel (k_energy3d_prof): one launch over [i_begin, i_end), no rho in HBM.  Every work
+// unit (tile x flush block) leaves a window of PROF_WIN bins; k_prof_reduce_windows adds the tiles of a flush block in
+// schedule order, k_radial_reduce_fb the flush blocks in index order -- fixed order, independent of scheduling and of how
+// the planes are cut into slabs.  *done = false (nothing written) when a unit touched more bins than its window holds:
+// the caller then takes the two-pass path.
+static int radial_profile_fused(iwb_handle* h, const iwb_params3d* p, const iwb_profile3d* prof, iwb_result* out, bool* done)
+{
+    *done = false;
+    auto t0 = std::chrono::steady_clock::now();
+    const int nb = prof->n_bins;
+    Scratch& c = h->scr[0];
+    cudaStream_t st = c.stream;
+    IWB_CUDA(cudaStreamSynchronize(st));
+    Launch3 L;
+    int rc = prepare_slab(h, p, c.h_coords, c.coords, c.partial, c.counter, st, nullptr, &L);
+    if (rc) return rc;
+    if (L.cfg_id != 1 || L.P.nspans <= 0) return IWB_OK;           // other geometry / empty grid: two-pass path
+    const int nfb_total = (p->n0 + FLUSH - 1) / FLUSH;
+    const int fb0 = L.fb0, fb1 = L.fb1, planes = p->i_end - p->i_begin;
+    const size_t nunits = (size_t)nfb_total * L.ntiles;
+    // device (doubles): thr[nb+1] | wsum[nunits][WIN] | fb_sum[nfb][nb] | fb_cnt[nfb][nb] | sum[nb] | cnt[nb] | wcnt (int) | wbase (int) | overflow
+    const size_t off_wsum = (size_t)nb + 1, off_fsum = off_wsum + nunits * PROF_WIN, off_fcnt = off_fsum + (size_t)nfb_total * nb,
+                 off_sum = off_fcnt + (size_t)nfb_total * nb, off_cnt = off_sum + nb, off_wcnt = off_cnt + nb,
+                 off_wbase = off_wcnt + (nunits * PROF_WIN + 1) / 2, off_ovf = off_wbase + (nunits + 1) / 2;
+    IWB_CUDA(c.prof.reserve((off_ovf + 1) * sizeof(double)));
+    IWB_CUDA(c.h_prof.reserve(((size_t)3 * nb + 4) * sizeof(double)));
+    IWB_CUDA(c.table.reserve((size_t)nfb_total * ROW * sizeof(double)));
+    IWB_CUDA(c.out.reserve(ROW_BYTES_MIN));
+    IWB_CUDA(c.h_out.reserve(ROW_BYTES_MIN));
+    double* dprof = (double*)c.prof.p;
+    double* hprof = (double*)c.h_prof.p;
+    for (int q = 0; q <= nb; ++q)
+        hprof[q] = (p->dtype == IWB_F64) ? profile_threshold_f64(prof->edges[q]) : profile_threshold_f32(prof->edges[q]);
+    IWB_CUDA(cudaMemcpyAsync(dprof, hprof, ((size_t)nb + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+    IWB_CUDA(cudaMemsetAsync(dprof + off_ovf, 0, sizeof(double), st));
+    K3Params& P = L.P;
+    P.prof_thr = dprof; P.prof_nb = nb;
+    P.prof_sum = dprof + off_wsum;
+    P.prof_cnt = (int*)(dprof + off_wcnt);
+    P.prof_base = (int*)(dprof + off_wbase);
+    P.prof_overflow = (unsigned int*)(dprof + off_ovf);
+    IWB_CUDA(cudaEventRecord(c.ev0, st));
+    cudaError_t e = (p->dtype == IWB_F64) ? launch_prof<IWB_F64>(P, h->sm_count, st) : launch_prof<IWB_F32_REF>(P, h->sm_count, st);
+    if (e != cudaSuccess) return fail(IWB_ERR_CUDA, std::string("k_energy3d_prof launch: ") + cudaGetErrorString(e));
+    k_reduce_tiles<<<fb1 - fb0, 32 * IWB_TILE_CHAINS, 0, st>>>(P.partial, (double*)c.table.p, fb0, L.ntiles, P.counter);
+    k_prof_reduce_windows<<<fb1 - fb0, PROF_FUSED_MAX_BINS, (size_t)L.ntiles * sizeof(int), st>>>(
+        P.prof_sum, P.prof_cnt, P.prof_base, fb0, L.ntiles, nb, dprof + off_fsum, (long long*)(dprof + off_fcnt));
+    k_radial_reduce_fb<<<(nb + 63) / 64, 64, 0, st>>>(dprof + off_fsum, (const long long*)(dprof + off_fcnt), fb0, fb1, nb,
+                                                      dprof + off_sum, (long long*)(dprof + off_cnt));
+    k_reduce_rows<<<1, 128, 0, st>>>((const double*)c.table.p + (size_t)fb0 * ROW, (double*)c.out.p, fb1 - fb0);
+    IWB_CUDA(cudaGetLastError());
+    IWB_CUDA(cudaEventRecord(c.ev1, st));
+    IWB_CUDA(cudaMemcpyAsync(hprof, dprof + off_sum, (size_t)2 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+    IWB_CUDA(cudaMemcpyAsync(hprof + 2 * nb, dprof + off_ovf, sizeof(double), cudaMemcpyDeviceToHost, st));
+    IWB_CUDA(cudaMemcpyAsync(c.h_out.p, c.out.p, ROW_BYTES_MIN, cudaMemcpyDeviceToHost, st));
+    IWB_CUDA(cudaStreamSynchronize(st));
+    unsigned int overflow = 0;
+    memcpy(&overflow, hprof + 2 * nb, sizeof(overflow));
+    if (overflow) return IWB_OK;                                  // bins narrower than a unit's window can hold
+    memcpy(prof->sum, hprof, (size_t)nb * sizeof(double));
+    memcpy(prof->count, hprof + nb, (size_t)nb * sizeof(int64_t));
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        unpack_row((const double*)c.h_out.p, p->nshell, out);
+        out->cnt_nan = (int64_t)planes * p->n1 * p->n2 - out->cnt_pos - out->cnt_neg - out->cnt_zero;
+        apply_reference_nonfinite(out, p->nshell);
+        float ms = 0;
+        IWB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+        out->kernel_ms = ms;
+        out->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    *done = true;
+    return IWB_OK;
+}
+
+extern "C" {
+
 int iwb_radial_profile3d(iwb_handle* h, const iwb_params3d* p, const iwb_profile3d* prof, iwb_result* out)
 {
     if (!h || !prof) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: null argument");
@@ -742,6 +823,19 @@ int iwb_radial_profile3d(iwb_handle* h, const iwb_params3d* p, const iwb_profile
         if (!(prof->edges[q + 1] > prof->edges[q])) return fail(IWB_ERR_INVALID, "iwb_radial_profile3d: edges must be strictly increasing");
     auto t0 = std::chrono::steady_clock::now();
     IWB_CUDA(cudaSetDevice(h->device));
+    // Bins inside the fused kernel when that is the faster route: measured on B200 (profiles/r2_f_rows_probe.log) the fused
+    // kernel takes 18.2 ms at n = 1024^3 against 19.4 ms for emit-then-bin (and needs no 1 GiB staging buffer), but 3.24
+    // against 2.56 ms at n = 512^3, and a work unit of a grid coarser than n ~ 400 spans more bins than a window holds.
+    // profile_fused: 0 never, 1 automatic (large volumes), 2 whenever the kernel can (tests).
+    const bool large = (double)(p->i_end - p->i_begin) * p->n1 * p->n2 >= 536870912.0;
+    if ((h->profile_fused == 2 || (h->profile_fused == 1 && large)) && nb <= PROF_FUSED_MAX_BINS &&
+        p->mode == IWB_MODE_EXACT && p->nshell <= 2) {
+        bool done = false;
+        rc = radial_profile_fused(h, p, prof, out, &done);
+        if (!rc && done) h->last_profile_path = 1;
+        if (rc || done) return rc;
+    }
+    h->last_profile_path = 2;
     Scratch& c = h->scr[0];
     cudaStream_t st = c.stream;
 

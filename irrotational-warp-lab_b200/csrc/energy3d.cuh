@@ -62,6 +62,12 @@ constexpr int FLUSH = IWB_FLUSH_PLANES;
 constexpr int SMEM_PAD = 8;         // guard doubles before and after the planes (lane 0 / lane 31 reads of idx -+ 1)
 constexpr int NPLANES = 11;
 constexpr int NEDGE = 18;           // one-sided coefficients a0 b0 c0 a1 b1 c1 of the three axes (shared-memory copy)
+// Fused radial profile (k_energy3d_prof): a work unit (tile x 16 planes) spans a few length units of r, i.e. a handful
+// of bins, so every warp keeps a WINDOW of PROF_WIN consecutive bins (sums + counts) in its slice of the flush scratch.
+constexpr int PROF_WIN = 14;                 // bins per window: 14 sums + 14 counts (7 doubles) <= ROW doubles per warp
+constexpr int PROF_FUSED_MAX_BINS = 144;     // thresholds of all bins live in shared memory
+constexpr int PROF_THR_S = PROF_FUSED_MAX_BINS + 1 + PROF_WIN + 1;   // thresholds + infinite padding behind the last edge
+static_assert(PROF_WIN + (PROF_WIN + 1) / 2 <= IWB_ROW_WIDTH, "a warp's profile window must fit its slice of the flush scratch");
 
 struct K3Params {
     int n0, n1, n2;
@@ -85,6 +91,13 @@ struct K3Params {
     double* rho_out;               // NULL or [i_end-i_begin][n1][n2]
     unsigned int* counter;         // dynamic work-item counter (0 at launch; reset by k_reduce_tiles)
     int i_zero, j_zero;            // index of the coordinate that is exactly 0 on axis 0 / 1 (-1: none): r == 0 is possible there
+    // fused radial profile (k_energy3d_prof only; see radial_profile.cuh for the binning rule)
+    const double* prof_thr;        // [prof_nb + 1] thresholds on s = r*r before the square root: r >= edges[q] <=> s >= prof_thr[q]
+    int prof_nb;                   // bins (<= PROF_FUSED_MAX_BINS)
+    double* prof_sum;              // [nfb_total][ntiles][PROF_WIN] per-unit window sums of rho
+    int* prof_cnt;                 // [nfb_total][ntiles][PROF_WIN] per-unit window point counts
+    int* prof_base;                // [nfb_total][ntiles] first bin of the unit's window
+    unsigned int* prof_overflow;   // set when a unit touches a bin beyond its window (the host then takes the two-pass path)
 };
 
 __host__ __device__ inline int tile_begin(int t, int nt, int n) { return (int)(((long long)t * n) / nt); }
@@ -124,9 +137,9 @@ struct Geo {
     static constexpr size_t SMEM_BYTES = (size_t(NPLANES) * PLANE + 2 * SMEM_PAD + NROWTAB * RJ + SCRATCH + NEDGE) * sizeof(double);
 };
 
-template <int DT, int NSH, int RJ, int NW, bool EMIT, int MINB = 1, int MODE = 0>
-__global__ void __launch_bounds__(NW * 32, MINB)
-k_energy3d(const __grid_constant__ K3Params P)
+// The kernel body; PROF adds the fused radial profile (k_energy3d_prof below), everything else is k_energy3d.
+template <int DT, int NSH, int RJ, int NW, bool EMIT, int MODE, bool PROF>
+__device__ __forceinline__ void energy3d_body(const K3Params& P)
 {
     using G = Geo<RJ, NW>;
     constexpr int PLANE = G::PLANE;
@@ -141,6 +154,8 @@ k_energy3d(const __grid_constant__ K3Params P)
     // One-sided (global face) coefficients live in shared memory: only the edge flavours of the tasks read them,
     // and as kernel parameters they would occupy 36 uniform registers that the interior loops need for their constants.
     double* const ec_s = scratch + G::SCRATCH;             // [3][6]: x, y, z -> a0 b0 c0 a1 b1 c1
+    double* const thr_s = ec_s + NEDGE;                    // PROF: [PROF_THR_S] bin thresholds on s, +inf behind the last edge
+    __shared__ int s_b0;                                   // PROF: first bin of the current window
 
     const int tx = threadIdx.x & 31;
     const int ty = threadIdx.x >> 5;
@@ -167,6 +182,9 @@ k_energy3d(const __grid_constant__ K3Params P)
         static_assert(sizeof(AxisCoef) == 8 * sizeof(double), "AxisCoef layout");
         const int axis = threadIdx.x / 6, q = threadIdx.x - 6 * axis;
         ec_s[threadIdx.x] = (&P.cx.h2)[8 * axis + 2 + q];
+    }
+    if (PROF) {
+        for (int q = threadIdx.x; q < PROF_THR_S; q += NW * 32) thr_s[q] = (q <= P.prof_nb) ? P.prof_thr[q] : INFINITY;
     }
     __syncthreads();
     auto step_arrive = [&]() { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar_addr) : "memory"); };
@@ -283,6 +301,96 @@ k_energy3d(const __grid_constant__ K3Params P)
         const int w0 = min(max(i0 - 1, 0), P.n0 - 3);
         const int pstart = max(0, w0 - 1);
 
+        // ---- fused radial profile (PROF): per-warp window of PROF_WIN bins in the warp's slice of the flush scratch ----
+        int pb = 0;                    // window-relative bins of the thread's four points at the previous plane, 8 bits each
+        bool beyond_seen = false;      // an output point of this thread lay beyond the window
+        int b0_reg = 0;                // first bin of the current window (copy of s_b0)
+        double* const win_sum = scratch + ty * ROW;                            // [PROF_WIN] sums of rho ...
+        int* const win_cnt = reinterpret_cast<int*>(win_sum + PROF_WIN);       // ... and [PROF_WIN] point counts
+        // Window of the flush block with planes [ia, ib): its first bin is the bin of the smallest s the block can hold,
+        // s_min = (min x*x + min y*y) + min z*z over the block's planes and the tile's output rows / columns (rounding is
+        // monotone, so every point of the block has s >= s_min).  Called by warp 0; publishes s_b0.
+        auto prof_rebase = [&](int ia, int ib) {
+            double m = INFINITY, ym = INFINITY;
+            for (int q = ia + tx; q < ib; q += 32) m = fmin(m, P.xx[q]);
+            for (int jr = 2 + tx; jr <= Tj + 1; jr += 32) ym = fmin(ym, yy_s[jr]);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                m = fmin(m, __shfl_xor_sync(0xffffffffu, m, off));
+                ym = fmin(ym, __shfl_xor_sync(0xffffffffu, ym, off));
+            }
+            const double smin = (DT == IWB_F64) ? (m + ym) + zzmin_s
+                                                : (double)__fadd_rn(__fadd_rn((float)m, (float)ym), (float)zzmin_s);
+            int below = 0;             // thresholds <= s_min (they are sorted)
+            for (int q0 = 0; q0 <= P.prof_nb; q0 += 32) {
+                const int q = q0 + tx;
+                below += __popc(__ballot_sync(0xffffffffu, q <= P.prof_nb && thr_s[q] <= smin));
+            }
+            if (tx == 0) s_b0 = max(below - 1, 0);
+        };
+        // Keys (window-relative bin, 255: in no bin) and rho of the warp's rows of one plane, filled by the tally; then ONE
+        // reduction for all of them: per row the three bins from the row's lowest one are summed over the lanes by
+        // independent shuffle trees (six dependent chains in flight instead of one after the other), lane 0 adds the
+        // results to the warp's window in fixed order; lanes further up -- rare: a row of 64 columns seldom spans more than
+        // three bins -- are handled bin by bin afterwards.  The order of every addition is fixed.
+        constexpr int NROWS = (RJ + NW - 1) / NW, PROF_KC = 3;
+        int pkey[NROWS][2];
+        double prho[NROWS][2];
+        auto prof_clear = [&]() {
+#pragma unroll
+            for (int it = 0; it < NROWS; ++it) { pkey[it][0] = 255; pkey[it][1] = 255; prho[it][0] = 0.0; prho[it][1] = 0.0; }
+        };
+        auto prof_reduce = [&]() {
+            int lo[NROWS];
+            double t[NROWS][PROF_KC];
+            int c[NROWS][PROF_KC];
+#pragma unroll
+            for (int it = 0; it < NROWS; ++it) lo[it] = __reduce_min_sync(0xffffffffu, min(pkey[it][0], pkey[it][1]));
+#pragma unroll
+            for (int it = 0; it < NROWS; ++it) {
+#pragma unroll
+                for (int k = 0; k < PROF_KC; ++k) {
+                    const bool m0 = pkey[it][0] == lo[it] + k && lo[it] != 255, m1 = pkey[it][1] == lo[it] + k && lo[it] != 255;
+                    t[it][k] = (m0 ? prho[it][0] : 0.0) + (m1 ? prho[it][1] : 0.0);
+                    c[it][k] = __popc(__ballot_sync(0xffffffffu, m0)) + __popc(__ballot_sync(0xffffffffu, m1));
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int it = 0; it < NROWS; ++it) {
+#pragma unroll
+                    for (int k = 0; k < PROF_KC; ++k) t[it][k] += __shfl_xor_sync(0xffffffffu, t[it][k], off);
+                }
+            }
+            if (tx == 0) {
+#pragma unroll
+                for (int it = 0; it < NROWS; ++it) {
+#pragma unroll
+                    for (int k = 0; k < PROF_KC; ++k)
+                        if (c[it][k]) { win_sum[lo[it] + k] += t[it][k]; win_cnt[lo[it] + k] += c[it][k]; }
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < NROWS; ++it) {
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const bool left = pkey[it][a] != 255 && pkey[it][a] >= lo[it] + PROF_KC;
+                    unsigned todo = __ballot_sync(0xffffffffu, left);
+                    while (todo) {
+                        const int b = __shfl_sync(0xffffffffu, pkey[it][a], __ffs(todo) - 1);
+                        const bool mine = left && pkey[it][a] == b;
+                        const unsigned same = __ballot_sync(0xffffffffu, mine);
+                        double v = mine ? prho[it][a] : 0.0;
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                        if (tx == 0) { win_sum[b] += v; win_cnt[b] += __popc(same); }
+                        todo &= ~same;
+                    }
+                }
+            }
+        };
+
         // ---- sums of one row's two points (reproduce_rodal_exact.py:57-61, 220-224) ---------------------
         // e is masked to +0.0 at the non-output columns (an AND with the column's all-ones / zero word), and the
         // accumulators are sum(e) and sum(|e|): E+ = (sum + sum|.|)/2, E- = (sum - sum|.|)/2, formed per thread at the
@@ -291,7 +399,46 @@ k_energy3d(const __grid_constant__ K3Params P)
         // Counts: every point is exactly one of neg / pos / zero / NaN; the first three are counted here in 8-bit
         // fields of one register (<= 64 points per thread and flush interval), NaN is derived by the host.  The zero
         // field also counts the masked non-output columns; the flush subtracts their (known) number.
-        auto tally2 = [&](const double (&e)[2], unsigned ya, double xxi) {
+        auto tally2 = [&](const double (&e)[2], const double (&rho)[2], unsigned ya, double xxi, int it) {
+            if (PROF) {
+                // Radial profile: bin q holds the points with edges[q] <= r < edges[q+1], i.e. thr[q] <= s < thr[q+1]
+                // (compared as integers: s >= +0).  A point's bin rarely moves by more than one from plane to plane, so
+                // the search starts at the bin it had one plane ago: one branch-free step, loops only when some lane of
+                // the warp needs more.  The row's keys and values are kept for prof_reduce (after both rows of the warp).
+                const double yyp = lds_f64<0>(ya);
+                double sp[2];
+                if (DT == IWB_F64) {
+                    const double sxy = xxi + yyp;
+                    sp[0] = sxy + zz0; sp[1] = sxy + zz1;
+                } else {
+                    const float sxy = __fadd_rn((float)xxi, (float)yyp);
+                    sp[0] = (double)__fadd_rn(sxy, (float)zz0); sp[1] = (double)__fadd_rn(sxy, (float)zz1);
+                }
+                const long long* const tw = reinterpret_cast<const long long*>(thr_s) + b0_reg;
+                const int om[2] = {om0, om1};
+                int rel[2] = {(pb >> (16 * it)) & 0xff, (pb >> (16 * it + 8)) & 0xff};
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const long long sb = __double_as_longlong(sp[a]);
+                    int r = rel[a];
+                    long long tlo = tw[r], thi = tw[r + 1];
+                    r += ((sb >= thi && r < PROF_WIN - 1) ? 1 : 0) - ((sb < tlo && r > 0) ? 1 : 0);
+                    tlo = tw[r]; thi = tw[r + 1];
+                    const bool unsettled = (sb < tlo && r > 0) || (sb >= thi && r < PROF_WIN - 1);
+                    if (__any_sync(0xffffffffu, unsettled)) {
+                        while (r > 0 && sb < tw[r]) --r;
+                        while (r < PROF_WIN - 1 && sb >= tw[r + 1]) ++r;
+                        tlo = tw[r]; thi = tw[r + 1];
+                    }
+                    rel[a] = r;
+                    const bool beyond = sb >= thi;                 // only with r == PROF_WIN - 1
+                    const bool inb = om[a] != 0 && sb >= tlo && !beyond;
+                    beyond_seen = beyond_seen || (beyond && om[a] != 0);
+                    pkey[it][a] = inb ? r : 255;
+                    prho[it][a] = rho[a];
+                }
+                pb = (pb & ~(0xffff << (16 * it))) | ((rel[0] | (rel[1] << 8)) << (16 * it));
+            }
             const int hm0 = __double2hiint(e[0]) & om0, hm1 = __double2hiint(e[1]) & om1;
             const double em0 = __hiloint2double(hm0, __double2loint(e[0]) & om0);
             const double em1 = __hiloint2double(hm1, __double2loint(e[1]) & om1);
@@ -363,12 +510,13 @@ k_energy3d(const __grid_constant__ K3Params P)
             const int iedge = (i == 0) ? 1 : ((i == P.n0 - 1) ? 2 : 0);
             const bool o_face = tile_edge || (iedge != 0);
             unsigned A = a_row0, ya = yy_row0;
+            if (PROF && doO) prof_clear();
 #if IWB_OC_UNROLL
 #pragma unroll
 #else
 #pragma unroll 1
 #endif
-            for (int jr = ty; jr < RJ; jr += NW, A += ROWB, ya += NW * 8) {
+            for (int jr = ty, it = 0; jr < RJ; jr += NW, A += ROWB, ya += NW * 8, ++it) {
                 const int jedge = (t_jlo && jr == 2) ? 1 : ((t_jhi && jr == Tj + 1) ? 2 : 0);
                 if (doO && jr >= 2 && jr <= Tj + 1) {
                     const unsigned Ai = A + o_pxi, Ap = A + o_pxp, Am = A + o_pxm, Ay = A + o_py;
@@ -435,7 +583,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                         if (cf1 & 16u) dst[32] = rho2[1];
                     }
                     const double e2[2] = {rho2[0] * P.dV, rho2[1] * P.dV};
-                    tally2(e2, ya, xxi);
+                    tally2(e2, rho2, ya, xxi, it);
                 }
                 if (doC && jr >= py_lo && jr <= py_hi) {
                     const unsigned Ah = A + o_ph, Aw = A + o_w;
@@ -464,6 +612,7 @@ k_energy3d(const __grid_constant__ K3Params P)
                     }
                 }
             }
+            if (PROF && doO) prof_reduce();
         };
 
         // P(p): phi(p) at the own columns and phi_x(p-1) = (phi(p) - phi(p-2)) / 2dx, which needs phi(p-2) of the
@@ -564,8 +713,31 @@ k_energy3d(const __grid_constant__ K3Params P)
         };
 
         // ---- block-level flush of the register sums into partial[fb][tile] ----------------
-        auto flush = [&](int fb, int i_last) {
+        auto flush = [&](int fb, int i_last, int i_end_march) {
             constexpr int NV = 6 + 3 * NSH;    // values actually reduced
+            if (PROF) {
+                // every warp has finished the tallies of this flush block (they arrived at the step barrier): warp 0 adds
+                // the windows in warp order, stores the unit's window and sets up the window of the next block
+                if (beyond_seen && b0_reg + PROF_WIN < P.prof_nb) atomicOr(P.prof_overflow, 1u);
+                beyond_seen = false;
+                if (ty == 0) {
+                    if (tx < PROF_WIN) {
+                        double a = 0.0;
+                        int c = 0;
+                        for (int w = 0; w < NW; ++w) {
+                            a += scratch[w * ROW + tx];
+                            c += reinterpret_cast<const int*>(scratch + w * ROW + PROF_WIN)[tx];
+                        }
+                        const size_t o = ((size_t)fb * ntiles + rnk) * PROF_WIN + tx;
+                        P.prof_sum[o] = a;
+                        P.prof_cnt[o] = c;
+                    }
+                    if (tx == 0) P.prof_base[(size_t)fb * ntiles + rnk] = b0_reg;
+                    __syncwarp();
+                    if (i_last + 1 < i_end_march) prof_rebase(i_last + 1, min(i_last + 1 + FLUSH, i_end_march));
+                }
+                __syncthreads();       // the windows have been read: the scratch may take the flush values
+            }
             double vals[NV];
             // E+ = (sum + sum|.|)/2 and E- = (sum - sum|.|)/2, per thread (halving is exact)
             vals[0] = (acc_sum + acc_abs) * 0.5; vals[1] = (acc_sum - acc_abs) * 0.5;
@@ -648,6 +820,13 @@ k_energy3d(const __grid_constant__ K3Params P)
             flush_from = i_last + 1;
 #pragma unroll
             for (int s = 0; s < NSHA; ++s) { sh_sum[s] = 0.0; sh_abs[s] = 0.0; sh_cnt[s] = 0; }
+            if (PROF) {
+                __syncthreads();       // the final reduction has read the scratch: it holds the windows again
+                if (tx < PROF_WIN + (PROF_WIN + 1) / 2) win_sum[tx] = 0.0;      // sums and (as zero bits) counts
+                __syncwarp();
+                b0_reg = s_b0;
+                pb = 0;
+            }
         };
 
         auto runP = [&](int p, int s3, double xp, double xxp) { taskP(p, s3, xp, xxp); };
@@ -661,6 +840,10 @@ k_energy3d(const __grid_constant__ K3Params P)
 
         // ---- prologue: everything O(i0) needs ----------------------------------------------------------
         __syncthreads();                 // yy_s visible
+        if (PROF) {                      // window of the first flush block of this march (published by the barriers below)
+            if (ty == 0) prof_rebase(i0, min(i1, (i0 / FLUSH + 1) * FLUSH));
+            if (tx < PROF_WIN + (PROF_WIN + 1) / 2) win_sum[tx] = 0.0;
+        }
         int produced = pstart - 1;
         bool px_last_done = false;
         {
@@ -676,6 +859,8 @@ k_energy3d(const __grid_constant__ K3Params P)
             if (produced == P.n0 - 1 && px_last_ok(i0)) { taskP_last(); px_last_done = true; }
             __syncthreads();
         }
+
+        if (PROF) { b0_reg = s_b0; pb = 0; beyond_seen = false; }
 
         // ---- march: one (split) barrier per output plane -----------------------------------------------
         const int plim = min(P.n0 - 1, i1 + 1);          // phi(i1+1) is the last plane this item needs
@@ -702,11 +887,27 @@ k_energy3d(const __grid_constant__ K3Params P)
             step_wait();
             if (doP) ++produced;
             if (doL) px_last_done = true;
-            if (((i + 1) & (FLUSH - 1)) == 0 || i == i1 - 1) flush(i / FLUSH, i);
+            if (((i + 1) & (FLUSH - 1)) == 0 || i == i1 - 1) flush(i / FLUSH, i, i1);
             m3 = m3p1;
         }
     }   // units of the span
     }   // spans
+}
+
+template <int DT, int NSH, int RJ, int NW, bool EMIT, int MINB = 1, int MODE = 0>
+__global__ void __launch_bounds__(NW * 32, MINB)
+k_energy3d(const __grid_constant__ K3Params P)
+{
+    energy3d_body<DT, NSH, RJ, NW, EMIT, MODE, false>(P);
+}
+
+// The same march with the radial profile of rho fused in (binning rule of radial_profile.cuh):
+// launched with Geo::SMEM_BYTES + PROF_THR_S doubles of dynamic shared memory.
+template <int DT, int NSH, int RJ, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_energy3d_prof(const __grid_constant__ K3Params P)
+{
+    energy3d_body<DT, NSH, RJ, NW, false, 0, true>(P);
 }
 
 // ---- fixed-order sum over tiles: partial[fb][tile][ROW] -> table[fb][ROW] ----------------------

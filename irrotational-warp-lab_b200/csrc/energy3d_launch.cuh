@@ -60,6 +60,27 @@ static cudaError_t launch_nsh(int nshell, int cfg, const K3Params& P, int sm_cou
     return launch_cfg<DT, IWB_MAX_SHELLS, EMIT, MODE>(cfg, P, sm_count, st);
 }
 
+// fused radial profile: default geometry, <= 2 shells, exact mode, no rho emission (everything else takes the two-pass path)
+template <int DT>
+static cudaError_t launch_prof(const K3Params& P, int sm_count, cudaStream_t st)
+{
+    auto kern = k_energy3d_prof<DT, 2, 40, 20>;
+    constexpr size_t smem = Geo<40, 20>::SMEM_BYTES + PROF_THR_S * sizeof(double);
+    static int ready[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !ready[dev]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) ready[dev] = 1;
+    }
+    int grid = sm_count;
+    if (grid > P.nspans) grid = P.nspans;
+    kern<<<grid, 20 * 32, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
 // defined in energy3d_fast.cu (IWB_MODE_FAST, float64 only)
 cudaError_t launch_k3_fast(int nshell, bool emit, int cfg, const K3Params& P, int sm_count, cudaStream_t st);
 

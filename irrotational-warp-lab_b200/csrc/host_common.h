@@ -113,12 +113,18 @@ struct iwb_handle {
     int k3_config = 0;         // kernel geometry variant (IWB_K3_CONFIG env override)
     int k3_static_pct = -1;    // share of the work units handed out as one large span per CTA; -1 = automatic (80 / 70 %),
                                // IWB_K3_STATIC_PCT env override
+    int last_profile_path = 0; // iwb_debug_profile_path
+    int profile_fused = 1;     // iwb_radial_profile3d bins inside the fused kernel: 1 = for large volumes (where it is the
+                               // faster route), 2 = whenever the kernel can, 0 = never (emit rho, bin it in a second
+                               // pass); IWB_PROFILE_FUSED env override
 };
 
 namespace iwb {
 AxisCoef make_axis_coef(double h);
 double shell_threshold_f64(double R);
 double shell_threshold_f32(double R);
+double profile_threshold_f64(double e);
+double profile_threshold_f32(double e);
 PhiConst make_phi_const(double rho, double sigma, double v, double eps, double sinh_rs, double cosh_rs);
 bool phi_fast_path_is_safe(const double* const coords[3], const int n[3], double rho, double sigma, double v, double eps,
                            double sinh_rs, double cosh_rs, int zero_index[3], bool float32_grid);

@@ -116,6 +116,40 @@ static __global__ void k_radial_reduce_sub(const double* __restrict__ part_sum, 
     }
 }
 
+// Fused path (k_energy3d_prof): per-unit windows [flush block][tile][PROF_WIN] with their first bin -> bins of every
+// flush block, the tiles added in schedule order (one block per flush block, one thread per bin; eight loads in flight).
+static __global__ void __launch_bounds__(PROF_FUSED_MAX_BINS) k_prof_reduce_windows(
+    const double* __restrict__ wsum, const int* __restrict__ wcnt, const int* __restrict__ wbase, int fb0, int ntiles,
+    int nb, double* __restrict__ fb_sum, long long* __restrict__ fb_cnt)
+{
+    extern __shared__ int s_base[];          // [ntiles]
+    const int fb = fb0 + blockIdx.x;
+    for (int t = threadIdx.x; t < ntiles; t += blockDim.x) s_base[t] = wbase[(size_t)fb * ntiles + t];
+    __syncthreads();
+    const int q = threadIdx.x;
+    if (q >= nb) return;
+    double a = 0.0;
+    long long c = 0;
+    for (int t0 = 0; t0 < ntiles; t0 += 8) {
+        double v[8];
+        int w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int t = t0 + u;
+            const int rel = (t < ntiles) ? q - s_base[t] : -1;
+            const bool in = rel >= 0 && rel < PROF_WIN;
+            const size_t o = ((size_t)fb * ntiles + (in ? t : 0)) * PROF_WIN + (in ? rel : 0);
+            v[u] = in ? wsum[o] : 0.0;
+            w[u] = in ? wcnt[o] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (w[u] >= 0) { a += v[u]; c += w[u]; }
+    }
+    fb_sum[(size_t)fb * nb + q] = a;
+    fb_cnt[(size_t)fb * nb + q] = c;
+}
+
 static __global__ void k_radial_reduce_fb(const double* __restrict__ fb_sum, const long long* __restrict__ fb_cnt,
                                           int fb0, int fb1, int nb, double* __restrict__ sum, long long* __restrict__ cnt)
 {

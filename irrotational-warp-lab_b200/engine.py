@@ -125,6 +125,7 @@ class Engine:
         del keep
         out = self._result_dict(r, p.nshell)
         out["bin_sum"], out["bin_count"] = sums[:nb], counts[:nb]
+        out["path"] = {1: "fused", 2: "two-pass"}.get(self._lib.iwb_debug_profile_path(self._h), "none")
         return out
 
     def energy3d_batch(self, points):

@@ -136,7 +136,7 @@ def radial_profile_3d(*, rho: float, sigma: float, v: float, extent: float, n: i
     return {"r_bins": 0.5 * (edges[:-1] + edges[1:]), "rho_avg": avg, "edges": edges, "bin_sum": tot, "bin_count": cnt,
             "grid": {"n": n, "extent": extent, "dx": dx, "dy": dx, "dz": dx},
             "energies": {"e_pos": res["e_pos"], "e_neg": res["e_neg"], "e_net": float(res["e_pos"] + res["e_neg"])},
-            "kernel_ms": res["kernel_ms"]}
+            "kernel_ms": res["kernel_ms"], "path": res.get("path")}
 
 
 def compute_tail_correction_3d(*, rho: float, sigma: float, v: float, extent: float, n: int, fit_r_min=None,

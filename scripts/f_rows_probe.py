@@ -14,7 +14,7 @@ for n in (256, 512, 1024):
         t0 = time.perf_counter()
         p = tail.radial_profile_3d(rho=5.0, sigma=4.0, v=1.0, extent=66.0, n=n)
         dt = time.perf_counter() - t0
-    print(f"radial_profile_3d n={n}: kernels {p['kernel_ms']:.2f} ms, call {dt*1e3:.2f} ms, "
+    print(f"radial_profile_3d n={n} ({p.get('path')}): kernels {p['kernel_ms']:.2f} ms, call {dt*1e3:.2f} ms, "
           f"{n**3/p['kernel_ms']/1e6:.1f} Gpts/s; points binned {int(p['bin_count'].sum())} of {n**3}; "
           f"e_net {p['energies']['e_net']:.6e}", flush=True)
 t = tail.compute_tail_correction_3d(rho=5.0, sigma=4.0, v=1.0, extent=66.0, n=512)

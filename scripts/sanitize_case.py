@@ -13,3 +13,6 @@ a = backend.compute_energy_axisymmetric(rho=5.0, sigma=4.0, v=1.0, extent=66.0, 
 print("axisym", a["energies"]["e_pos"])
 s = slice2d.compute_slice_z0(rho=10.0, sigma=3.0, v=1.5, extent=20.0, n=41)
 print("slice", slice2d.integrate_signed(s, s.dx, s.dy))
+from irrotational_warp_lab_b200 import tail
+p = tail.radial_profile_3d(rho=5.0, sigma=4.0, v=1.0, extent=66.0, n=45, n_bins=30)
+print("radial profile (fused kernel)", int(p["bin_count"].sum()))
