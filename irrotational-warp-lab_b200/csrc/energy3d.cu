@@ -45,8 +45,8 @@ static int validate(const iwb_params3d* p)
     if (p->nshell < 0 || p->nshell > IWB_MAX_SHELLS) return fail(IWB_ERR_INVALID, "energy3d: nshell out of range");
     if (!(p->dx > 0.0) || !(p->dy > 0.0) || !(p->dz > 0.0)) return fail(IWB_ERR_INVALID, "energy3d: spacings must be > 0");
     {
-        // the kernel tallies rho and scales by dV at the flush; its exact zero / sign classification of rho * dV assumes
-        // that only a rho below 2^-511 can underflow in that product
+        // e = rho * dV is what the reference classifies and sums; a cell volume outside this range makes that product
+        // under- or overflow wholesale (an unusable grid), and the call refuses it instead of returning zeros / infinities
         const double dV = (p->dx * p->dy) * p->dz;
         if (!(dV >= 0x1p-400 && dV <= 0x1p400)) return fail(IWB_ERR_INVALID, "energy3d: dx*dy*dz outside [2^-400, 2^400]");
     }
