@@ -32,7 +32,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=o
 # translation unit -> extra flags
 UNITS = {
     "core.cu": [],
-    "energy3d.cu": ["-fmad=false"] + ([f"-DIWB_DBG={os.environ['IWB_DBG']}"] if os.environ.get("IWB_DBG") else []) + ([f"-DIWB_BARRIER_BACKOFF_NS={os.environ['IWB_BACKOFF']}"] if os.environ.get("IWB_BACKOFF") else []),
+    "energy3d.cu": ["-fmad=false"],
     "energy3d_fast.cu": ["-fmad=true"],
     "planar.cu": ["-fmad=false"],
     "einstein.cu": ["-fmad=false"],

@@ -1,5 +1,6 @@
-"""Throughput of iwb_energy3d_batch for grids of a few sizes (IWB_BATCH_SPLIT=0|1|N selects how a batch of small grids
-shares the SMs).  usage: python scripts/batch_probe.py [npoints] [reps]   (development aid)"""
+"""Throughput of iwb_energy3d_batch for grids of a few sizes.  usage: python scripts/batch_probe.py [npoints] [reps]
+(development aid; the IWB_BATCH_SPLIT switch it was written for -- SM partitions per concurrent evaluation -- was measured
+with it and removed, profiles/r2_ab18_batch_split.log)"""
 import hashlib
 import os
 import sys
@@ -26,5 +27,5 @@ for n in (100, 256, 400, 512):
         res = eng.energy3d_batch(pts)
         best = min(best, time.perf_counter() - t0)
     digest = hashlib.sha256(repr([(r["e_pos"], r["e_neg"], r["cnt_neg"], r["cnt_pos"]) for r in res]).encode()).hexdigest()[:16]
-    print(f"batch of {npts} x n={n}^3 split={os.environ.get('IWB_BATCH_SPLIT', 'default')}: {best*1e3:.3f} ms = "
+    print(f"batch of {npts} x n={n}^3: {best*1e3:.3f} ms = "
           f"{npts/best:.0f} evaluations/s = {npts*n**3/best/1e9:.1f} Gpoints/s; results sha {digest}", flush=True)

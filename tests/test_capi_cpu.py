@@ -146,8 +146,7 @@ def test_column_tiles_partition_the_axis():
 
 def test_row_tiles_partition_the_axis():
     """tiles_j / tile_begin_j (csrc/energy3d.cuh) for the default 40-row region: an even split into tiles of at most 36
-    output rows (default build), or -- IWB_JFACE builds -- 38 rows in the two tiles at the j faces and one tile row less
-    where that suffices."""
+    output rows (tiles of 38 rows at the j faces were measured twice and rejected)."""
     lib = _capi.load()
     buf = (C.c_int * 512)()
     for n in list(range(3, 500)) + [512, 1000, 1023, 1024, 1025, 2048, 4096]:
@@ -155,14 +154,7 @@ def test_row_tiles_partition_the_axis():
         b = list(buf)[: nt + 1]
         assert b[0] == 0 and b[-1] == n
         sizes = [b[t + 1] - b[t] for t in range(nt)]
-        assert min(sizes) >= 1
-        even_split = -(-n // 36)
-        if nt == even_split and max(sizes) <= 36:
-            continue                                   # default build
-        if nt == 1:
-            assert n <= 40
-        else:
-            assert sizes[0] <= 38 and sizes[-1] <= 38 and all(s <= 36 for s in sizes[1:-1])
-            cap_fewer = 40 if nt == 2 else 2 * 38 + (nt - 3) * 36
-            assert n > cap_fewer
-    assert lib.iwb_debug_tiles_j(256, buf, 512) in (7, 8) and lib.iwb_debug_tiles_j(1024, buf, 512) == 29
+        assert min(sizes) >= 1 and max(sizes) <= 36
+        assert nt == -(-n // 36)                       # no tile row more than needed
+        assert max(sizes) - min(sizes) <= 1            # an even split
+    assert lib.iwb_debug_tiles_j(256, buf, 512) == 8 and lib.iwb_debug_tiles_j(1024, buf, 512) == 29
