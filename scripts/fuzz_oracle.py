@@ -1,5 +1,5 @@
 """Seeded random configurations of the 3D evaluator against the C oracle (development aid; GPU box).
-usage: python scripts/fuzz_oracle.py [ncases] [seed]"""
+usage: python scripts/fuzz_oracle.py [ncases] [seed] [n_lo] [n_hi]"""
 import os
 import sys
 
@@ -11,13 +11,15 @@ from oracle import oracle_c  # noqa: E402
 
 ncases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 2026)
+n_lo = int(sys.argv[3]) if len(sys.argv) > 3 else 9
+n_hi = int(sys.argv[4]) if len(sys.argv) > 4 else 98
 bad = 0
 for c in range(ncases):
     rho = float(np.round(rng.uniform(0.5, 8.0), 3))
     sigma = float(np.round(rng.uniform(0.6, 12.0), 3))
     v = float(np.round(rng.uniform(-3.0, 3.0), 3))
     extent = float(np.round(rho * rng.uniform(1.5, 14.0), 3))
-    n = int(rng.integers(9, 98))
+    n = int(rng.integers(n_lo, n_hi))
     dtype = "float32" if c % 5 == 4 else "float64"
     kw = dict(rho=rho, sigma=sigma, v=v, extent=extent, n=n)
     shells = [2.0 * rho, 0.5 * extent]
