@@ -377,6 +377,9 @@ def main(argv=None):
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--exchange", choices=["auto", "peer", "nccl"], default="auto",
                     help="N > 1: how the chain sums travel (NVLink peer stores fused behind the kernel, or NCCL all-gather)")
+    ap.add_argument("--shard", choices=["tiles", "slab"], default="tiles",
+                    help="N > 1: interleaved tile shards (default) or slabs of axis 0 (the north star's wording; 2-plane halo "
+                         "recomputed analytically, NCCL all-gather of the table rows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args(argv)
     if args.impl == "reference":
@@ -414,7 +417,7 @@ def main(argv=None):
     dx = float(x[1] - x[0])
     # N > 1: interleaved tile shards (every rank marches its tiles along the whole of axis 0); the slab decomposition
     # is the fall-back for a world size that does not divide the 16 tile chains
-    tiles = sharding.tile_shard(world, rank) if world > 1 else None
+    tiles = sharding.tile_shard(world, rank) if (world > 1 and args.shard == "tiles") else None
     i_begin, i_end = (0, n) if (world == 1 or tiles is not None) else sharding.slab_bounds(n, world)[rank]
     nfb = sharding.num_flush_blocks(n)
     r0, r1 = sharding.rows_of_slab(i_begin, i_end)
@@ -531,7 +534,7 @@ def main(argv=None):
     def api_step():
         if world > 1:
             return distributed.compute_energy_3d_sharded(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, n=n, shells=SHELLS,
-                                                         exchange=args.exchange)
+                                                         exchange=args.exchange, shard=args.shard)
         return backend.compute_energy_3d(rho=RHO, sigma=SIGMA, v=V, extent=EXTENT, n=n, shells=SHELLS)
 
     for _ in range(warmup):
