@@ -157,7 +157,8 @@ int iwb_reduce_chains(iwb_handle *h, const double *gathered_device, int tile_str
  * iwb_energy3d_tiles_exchange_async is COLLECTIVE: every rank of the group calls it the same number of times with
  * tile_stride = world, tile_first = rank; it enqueues k_energy3d, the push of the chain sums and the combine on `stream`
  * and leaves the final row (IWB_ROW_WIDTH doubles) in `row_device` without synchronising.  iwb_read_row copies such a row
- * to the host (blocking) and unpacks it. */
+ * to the host (blocking) and unpacks it.  A rank whose peers do not signal within 60 s (a peer process died, or did not
+ * make the call) traps instead of spinning for ever: the next synchronisation on `stream` reports a CUDA error. */
 #define IWB_PEER_HANDLE_BYTES 64
 typedef struct iwb_peer iwb_peer;
 int iwb_peer_create(iwb_handle *h, int rank, int world, int nfb_max, iwb_peer **out, void *handle_out);
@@ -199,7 +200,8 @@ int iwb_energy3d_batch(iwb_handle *h, int npoints, const iwb_params3d *pts, iwb_
 
 /* Radial-shell profile of rho_adm on the 3D grid: sum and point count over edges[k] <= r < edges[k+1], the binning
  * rule of compute_radial_average_z0 (src/irrotational_warp/tail.py:46-80) applied to the field of compute_energy_3d
- * (SURVEY.md §8 f3).  The field is emitted and re-read in passes of <= 1 GiB on the device and never reaches the host.
+ * (SURVEY.md §8 f3).  Large volumes (>= 2^29 points, <= 144 bins, <= 2 shells) are binned inside the fused kernel itself
+ * (k_energy3d_prof); otherwise the field is emitted and re-read in passes of <= 1 GiB on the device.  It never reaches the host.
  * `out` (may be NULL) receives the energies / counts of the same evaluation.  Deterministic and independent of the
  * pass size; sums over [i_begin, i_end) only, so slabs can be added on the host. */
 typedef struct {

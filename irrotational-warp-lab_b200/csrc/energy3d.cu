@@ -672,6 +672,14 @@ static int launch_exchange(iwb_handle* h, iwb_peer* pr, const Launch3& L, int nf
     X.epoch = epoch; X.rank = pr->rank; X.stride = S; X.nfb = nfb;
     X.table = pr->table; X.row = row_device;
     X.ticket = (unsigned int*)(pr->table + (size_t)pr->nfb_max * ROW);
+    {
+        static const double timeout_s = [] {
+            const char* e = getenv("IWB_EXCHANGE_TIMEOUT_S");
+            const double v = e ? atof(e) : 60.0;
+            return (v > 0.0 && v < 86400.0) ? v : 60.0;
+        }();
+        X.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+    }
     k_chain_sums_push<<<nfb, 32 * (IWB_TILE_CHAINS / S), 0, st>>>(L.P.partial, X.peers, 0, nfb, L.ntiles, first, S,
                                                                   IWB_TILE_CHAINS, L.P.counter);
     k_exchange_combine<<<nfb, 32 * IWB_TILE_CHAINS, 0, st>>>(X);

@@ -1034,6 +1034,7 @@ struct ExchParams {
     double* table;                           // [nfb][ROW] scratch
     double* row;                             // [ROW] result
     unsigned int* ticket;                    // 0 at launch; the last block resets it
+    unsigned long long timeout_ns;           // longest wait for the peers' flags before the kernel traps
 };
 
 static __global__ void __launch_bounds__(1024) k_exchange_combine(const ExchParams X)
@@ -1046,10 +1047,17 @@ static __global__ void __launch_bounds__(1024) k_exchange_combine(const ExchPara
     if (blockIdx.x == 0 && threadIdx.x < X.stride)
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(X.peers.flag[threadIdx.x] + X.rank), "l"(X.epoch) : "memory");
     if (threadIdx.x < X.stride) {
-        unsigned long long seen;
-        do {
+        // A peer that never signals (its process died, or it never made the call) must not leave this GPU spinning for
+        // ever: after the time-out (60 s; IWB_EXCHANGE_TIMEOUT_S in the environment of the process) the kernel traps, the
+        // stream reports an error and the host call fails loudly.
+        unsigned long long seen, t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(X.flag_local + threadIdx.x) : "memory");
-        } while (seen < X.epoch);
+            if (seen >= X.epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > X.timeout_ns) __trap();
+        }
     }
     __syncthreads();
     const int nlc = nch / X.stride;
